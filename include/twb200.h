@@ -1,0 +1,161 @@
+/* twb200.h — C ABI of libtwb200.so, the B200-native (sm_100a) Whisper teacher-inference path.
+ *
+ * Drop-in boundary for the hot path of forbes110/taiwan-whisper.  The reference reaches this
+ * arithmetic through two Python calls into HuggingFace transformers:
+ *   feature_extractor(raw_speech, sampling_rate=16000)
+ *       ref: training/run_pseudo_labelling.py:739, prefiltering/validator_inference.py:57-60
+ *   model.generate(input_features, max_length=, num_beams=1, return_timestamps=, language=, task=)
+ *       ref: training/run_pseudo_labelling.py:864-876,917-918, prefiltering/validator_inference.py:41-47,78
+ * Each entry point below names the reference interface it replaces.  The Python host
+ * (taiwan-whisper_b200/host.py, ctypes) mirrors those two call signatures on top of this ABI;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: plain C types; every call returns 0 (TW_OK) or a negative TW_E_* code and the
+ * message is read with tw_last_error(ctx); no C++ exception crosses the ABI.  Calls are
+ * stream-ordered and asynchronous unless they take host output buffers.  A ctx is bound to one
+ * device and is NOT thread-safe (one ctx per device per process, as `accelerate launch` gives
+ * one process per GPU: ref training/run-pseudo-labelling.sh:19).  Buffers passed in are owned by
+ * the caller; workspace, KV cache and CUDA graphs are owned by the ctx / model.
+ * There is no CPU fallback: without a CUDA device every call fails with TW_E_CUDA.
+ */
+#ifndef TWB200_H
+#define TWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TW_API __attribute__((visibility("default")))
+#else
+#define TW_API
+#endif
+
+#define TWB200_ABI_VERSION 1
+
+enum {
+    TW_OK = 0,
+    TW_E_INVALID = -1,     /* bad argument (maps to ValueError in the host) */
+    TW_E_CUDA = -2,        /* CUDA runtime / driver failure */
+    TW_E_NOMEM = -3,
+    TW_E_UNSUPPORTED = -4, /* e.g. num_beams != 1 (maps to NotImplementedError) */
+    TW_E_SHAPE = -5,       /* feature length != 3000 etc. (HF raises ValueError) */
+    TW_E_STATE = -6
+};
+
+enum { TW_F32 = 0, TW_BF16 = 1, TW_I16 = 2, TW_I32 = 3 };
+
+#define TW_N_SAMPLES 480000 /* 30 s @ 16 kHz */
+#define TW_N_FRAMES 3000
+#define TW_N_CTX 1500
+
+typedef struct tw_ctx tw_ctx;
+typedef struct tw_model tw_model;
+
+TW_API int tw_abi_version(void);
+TW_API int tw_ctx_create(int device, tw_ctx** out);
+TW_API void tw_ctx_destroy(tw_ctx* ctx);
+TW_API const char* tw_last_error(const tw_ctx* ctx);
+/* number of kernels this ctx has launched so far (evidence for bench.py's gpu_launches) */
+TW_API uint64_t tw_launch_count(const tw_ctx* ctx);
+
+/* ---- log-mel front end ------------------------------------------------------------------
+ * Replaces WhisperFeatureExtractor.__call__ (transformers/models/whisper/
+ * feature_extraction_whisper.py:135-164; in-reference twin training/flax/distil_whisper/
+ * pipeline.py:40-58), called at ref training/run_pseudo_labelling.py:739 and
+ * prefiltering/validator_inference.py:57-60, including the pad/trim to 480000 samples of
+ * ref prefiltering/validator_inference.py:131-137.
+ *   pcm        device, [B, pcm_stride] samples, int16 (dequantised x/32768) or float32
+ *   n_valid    device int32 [B] or NULL: samples beyond n_valid[b] (and beyond pcm_stride) read as 0;
+ *              values > 480000 are truncated
+ *   out        device float32 [B, n_mel, 3000]
+ * n_mel must be 80 or 128. */
+TW_API int tw_logmel(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B,
+              int n_mel, float* out, void* stream);
+
+/* ---- model -------------------------------------------------------------------------------
+ * Replaces WhisperForConditionalGeneration (encoder: modeling_whisper.py:593-647, decoder
+ * :691-798, tied LM head :1081) as loaded at ref training/run_pseudo_labelling.py:566-577 and
+ * prefiltering/validator_inference.py:30. */
+typedef struct {
+    int32_t d_model, ffn, heads, enc_layers, dec_layers, n_mel, vocab, max_target; /* max_target: 448 */
+    int32_t dtype;    /* TW_BF16: bf16 storage, fp32 accumulate (tcgen05); TW_F32: fp32 check mode (CUDA-core FMA) */
+    int32_t max_batch;
+} tw_model_desc;
+
+/* One named tensor.  Names are the HF state_dict keys ("model.encoder.conv1.weight", ...).
+ * Pointers are DEVICE pointers borrowed only during tw_model_load: the model keeps its own
+ * repacked copies, so the caller may free them afterwards.  dtype: TW_F32 or TW_BF16. */
+typedef struct {
+    const char* name;
+    const void* ptr;
+    int32_t dtype;
+    int64_t numel;
+} tw_weight;
+
+TW_API int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table, size_t n, tw_model** out);
+TW_API void tw_model_free(tw_model* m);
+/* bytes of device memory the model holds for weights + workspace at max_batch */
+TW_API size_t tw_model_bytes(const tw_model* m);
+
+/* WhisperEncoder.forward on B windows: mel float32 [B, n_mel, 3000] (device) ->
+ * enc_out [B, 1500, d_model] in the model dtype (device).  tap_layer >= 0 additionally copies the
+ * fp32 residual stream after `tap_layer` layers (0 = after the conv stem + positions) to tap_out
+ * [B,1500,d] float32 (parity tests); pass -1 / NULL otherwise. */
+TW_API int tw_encode(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, void* stream);
+
+/* Logits rules of WhisperGenerationMixin._retrieve_logit_processors (generation_whisper.py:1774-1812;
+ * processors logits_process.py:1812-2044).  Host arrays, copied during the call. */
+typedef struct {
+    const int32_t* suppress;       /* SuppressTokensLogitsProcessor ids */
+    int32_t n_suppress;
+    const int32_t* begin_suppress; /* SuppressTokensAtBeginLogitsProcessor ids (first generated position only) */
+    int32_t n_begin_suppress;
+    int32_t eos, pad;
+    int32_t timestamp_begin;       /* >= 0 enables WhisperTimeStampLogitsProcessor; -1 = return_timestamps=False */
+    int32_t no_timestamps;         /* <|notimestamps|> id */
+    int32_t max_initial_timestamp_index; /* < 0: unset */
+} tw_rules;
+
+/* KV-cached greedy decoding of GenerationMixin._sample (generation/utils.py:2658-2805) for one
+ * 30 s window per row.
+ *   enc_out     device [B,1500,d] model dtype (from tw_encode)
+ *   prompt      host int32 [P]: forced tokens <|sot|><|zh|><|transcribe|>[<|notimestamps|>]
+ *               (_retrieve_init_tokens, generation_whisper.py:1455-1608), same for every row
+ *   max_length  total length incl. prompt (HF max_length); P < max_length <= max_target
+ *   out_tokens  device int32 [B, max_length - P]: generated ids; after a row's EOS: pad
+ *   out_lengths device int32 [B]: number of generated tokens before EOS
+ *   forced      device int32 [B, max_length - P] or NULL: teacher forcing (diagnostic) — token fed
+ *               back at each step instead of the argmax; out_tokens still records the argmax
+ *   logits_tap  device float32 [tap_steps, B, vocab] or NULL: post-rules logits of the first steps */
+TW_API int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* prompt, int P, const tw_rules* rules,
+                     int max_length, int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced,
+                     float* logits_tap, int tap_steps, void* stream);
+
+/* The whole path with HOST buffers: pinned (or pageable) int16 PCM in, token ids out —
+ * H2D copy, log-mel, encoder, cross-K/V, greedy decode, D2H copy, stream-synchronised on return.
+ * One call = the reference's feature_extractor(...) + model.generate(...) for a batch.
+ *   pcm_host        int16 [B, 480000]
+ *   out_tokens_host int32 [B, max_length - P], out_lengths_host int32 [B] */
+TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_valid_host, int B,
+                       const int32_t* prompt, int P, const tw_rules* rules, int max_length,
+                       int32_t* out_tokens_host, int32_t* out_lengths_host, void* stream);
+
+/* Per-stage device time of the last tw_transcribe_host / tw_encode / tw_decode_greedy call in ms
+ * (CUDA events on the call's stream): [0] log-mel, [1] encoder, [2] cross-K/V, [3] decode, [4] total. */
+TW_API int tw_last_stage_ms(tw_model* m, float out_ms[5]);
+
+/* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
+ * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,
+ * 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
+ * (dtype), 2 C(f32) += , 3 C(f32) = GELU(.) + pos[row % pos_period], 4 C(f32) = . */
+TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
+                  int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWB200_H */

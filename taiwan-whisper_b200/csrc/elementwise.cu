@@ -1,0 +1,188 @@
+// LayerNorm, conv im2col gathers, token embedding, KV append.
+#include "kernels.cuh"
+
+namespace tw {
+
+// ---- LayerNorm over the fp32 residual stream: one warp per row, two-pass (mean, then centred
+// variance) in fp32, biased variance, eps 1e-5 (torch nn.LayerNorm; ref flax layers.py:759-815).
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 T* __restrict__ out, int M, int d) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float* xr = x + (int64_t)row * d;
+    // d <= 1280 here: keep the row in registers (float4 per lane, up to 10 chunks)
+    constexpr int MAXC = 10;
+    float4 v[MAXC];
+    const int nchunk = d >> 2;          // d % 4 == 0
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nchunk) {
+            v[c] = *reinterpret_cast<const float4*>(xr + 4 * i);
+            s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nchunk) {
+            const float a = v[c].x - mean, b = v[c].y - mean, e = v[c].z - mean, f = v[c].w - mean;
+            q += (a * a + b * b) + (e * e + f * f);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    T* orow = out + (int64_t)row * d;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nchunk) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * i);
+            const float4 bb = *reinterpret_cast<const float4*>(beta + 4 * i);
+            const float o0 = (v[c].x - mean) * rstd * g.x + bb.x;
+            const float o1 = (v[c].y - mean) * rstd * g.y + bb.y;
+            const float o2 = (v[c].z - mean) * rstd * g.z + bb.z;
+            const float o3 = (v[c].w - mean) * rstd * g.w + bb.w;
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + 4 * i) = make_float4(o0, o1, o2, o3);
+            } else {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&p0);
+                pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(orow) + 4 * i) = pk;
+            }
+        }
+    }
+}
+
+template <typename T>
+void layernorm(const float* x, const float* gamma, const float* beta, T* out, int M, int d, cudaStream_t st) {
+    if (M <= 0) return;
+    layernorm_kernel<T><<<ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, out, M, d);
+}
+template void layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
+template void layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, cudaStream_t);
+
+// ---- conv1 im2col: out[(b,t)][tap*n_mel + c] = mel[b][c][t + tap - 1]  (0 outside), cast to T —
+// the same rounding as the reference's `input_features.to(torch_dtype)`
+// (ref: training/run_pseudo_labelling.py:918).  Tile transpose through shared memory:
+// reads are contiguous in t, writes contiguous in c.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_conv1_kernel(const float* __restrict__ mel, T* __restrict__ out, int n_mel) {
+    __shared__ float tile[32][33 + 2];      // [c][t - t0 + 1], halo of 1 each side
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float* src = mel + (int64_t)b * n_mel * TW_N_FRAMES;
+    for (int cc = ty; cc < 32; cc += 8) {
+        const int c = c0 + cc;
+        for (int tt = tx; tt < 34; tt += 32) {
+            const int t = t0 + tt - 1;
+            float v = 0.0f;
+            if (c < n_mel && t >= 0 && t < TW_N_FRAMES) v = src[(int64_t)c * TW_N_FRAMES + t];
+            tile[cc][tt] = v;
+        }
+    }
+    __syncthreads();
+    const int K = 3 * n_mel;
+    for (int tt = ty; tt < 32; tt += 8) {
+        const int t = t0 + tt;
+        if (t >= TW_N_FRAMES) continue;
+        T* orow = out + ((int64_t)b * TW_N_FRAMES + t) * K;
+        const int c = c0 + tx;
+        if (c < n_mel) {
+#pragma unroll
+            for (int tap = 0; tap < 3; ++tap) orow[tap * n_mel + c] = from_f32<T>(tile[tx][tt + tap]);
+        }
+    }
+}
+
+template <typename T>
+void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st) {
+    dim3 grid(ceil_div(TW_N_FRAMES, 32), ceil_div(n_mel, 32), B);
+    im2col_conv1_kernel<T><<<grid, 256, 0, st>>>(mel, out, n_mel);
+}
+template void im2col_conv1<float>(const float*, float*, int, int, cudaStream_t);
+template void im2col_conv1<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, cudaStream_t);
+
+// ---- conv2 im2col (stride 2, pad 1): out[(b,t')][tap*d + c] = h0[(b, 2t'+tap-1)][c]; 16-byte copies
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_conv2_kernel(const T* __restrict__ h0, T* __restrict__ out, int d, int64_t total_vec) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int dv = d / VEC;                        // d % 8 == 0
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % dv);
+        const int64_t r = i / dv;                  // (b*1500 + t')*3 + tap
+        const int tap = (int)(r % 3);
+        const int64_t bt = r / 3;
+        const int tp = (int)(bt % TW_N_CTX);
+        const int64_t b = bt / TW_N_CTX;
+        const int t = 2 * tp + tap - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t >= 0 && t < TW_N_FRAMES)
+            v = *reinterpret_cast<const uint4*>(h0 + ((int64_t)b * TW_N_FRAMES + t) * d + (int64_t)cv * VEC);
+        *reinterpret_cast<uint4*>(out + (bt * 3 + tap) * d + (int64_t)cv * VEC) = v;
+    }
+}
+
+template <typename T>
+void im2col_conv2(const T* h0, T* out, int B, int d, cudaStream_t st) {
+    constexpr int VEC = 16 / sizeof(T);
+    const int64_t total = (int64_t)B * TW_N_CTX * 3 * (d / VEC);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col_conv2_kernel<T><<<blocks, 256, 0, st>>>(h0, out, d, total);
+}
+template void im2col_conv2<float>(const float*, float*, int, int, cudaStream_t);
+template void im2col_conv2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, cudaStream_t);
+
+// ---- decoder input: x[b] = E[tok[b]] + P[pos]  (HF WhisperDecoder.forward :738-760)
+template <typename T>
+__global__ void embed_kernel(const int32_t* __restrict__ tok, const T* __restrict__ E, const T* __restrict__ P, int pos,
+                             float* __restrict__ x, int d) {
+    const int b = blockIdx.x;
+    const int t = tok[b];
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[(int64_t)b * d + i] = to_f32(E[(int64_t)t * d + i]) + to_f32(P[(int64_t)pos * d + i]);
+}
+template <typename T>
+void embed_tokens(const int32_t* tok, const T* E, const T* P, int pos, float* x, int B, int d, cudaStream_t st) {
+    embed_kernel<T><<<B, 256, 0, st>>>(tok, E, P, pos, x, d);
+}
+template void embed_tokens<float>(const int32_t*, const float*, const float*, int, float*, int, int, cudaStream_t);
+template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, int, float*, int, int,
+                                          cudaStream_t);
+
+// ---- self-attention KV cache append: cache[b][pos][0:2d] = qkv[b][d:3d]
+template <typename T>
+__global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, int pos, int d, int max_len) {
+    const int b = blockIdx.x;
+    const T* src = qkv + (int64_t)b * 3 * d + d;
+    T* dst = cache + ((int64_t)b * max_len + pos) * 2 * d;
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) dst[i] = src[i];
+}
+template <typename T>
+void kv_append(const T* qkv, T* cache, int pos, int B, int d, int max_len, cudaStream_t st) {
+    kv_append_kernel<T><<<B, 256, 0, st>>>(qkv, cache, pos, d, max_len);
+}
+template void kv_append<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+
+__global__ void copy_f32_kernel(const float4* __restrict__ s, float4* __restrict__ d, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st) {
+    const int64_t n4 = n / 4;     // callers pass multiples of 4
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 0) copy_f32_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4);
+}
+
+}  // namespace tw

@@ -1,0 +1,376 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias), bf16 x bf16 -> fp32.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D loads of A (128 x 64) and W (BN x 64) tiles, 128-byte
+//                                swizzle, into a 4-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) from
+//                                shared-memory descriptors into a double-buffered TMEM accumulator and
+//                                tcgen05.commit's the ring slot / the accumulator to mbarriers
+//   warps 2-5   epilogue       : tcgen05.ld the accumulator (thread = row, 32 columns per load), fused
+//                                bias / exact GELU / fp32 residual add / sinusoid add, 32-byte-sector stores;
+//                                overlaps the next tile's MMAs through the second TMEM buffer
+// Edge tiles rely on TMA out-of-bounds zero fill (M, N, K tails) and guarded stores.
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "kernels.cuh"
+
+namespace tw {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;            // 64 bf16 = 128 bytes = one swizzle row
+constexpr int TC_THREADS = 192;      // 6 warps
+constexpr int TC_EPI_WARP0 = 2;
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int A_BYTES = TC_BM * TC_BK * 2;
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered fp32 accumulator (power of two >= 32)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+// a/b K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K, GemmEpi epi) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int k_blocks = (K + TC_BK - 1) / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tmem_full[s]), 1);
+            mbar_init(smem_u32(&tmem_empty[s]), 4);      // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                    tma_load_2d(&map_a, fb, sa, kb * TC_BK, m_blk * TC_BM);
+                    tma_load_2d(&map_w, fb, sa + Cfg::A_BYTES, kb * TC_BK, n_blk * BN);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t a_desc = make_sw128_desc(sa);
+                    const uint64_t b_desc = make_sw128_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                        tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(&tmem_full[acc]));                      // accumulator ready
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+            tc_fence_after();
+            const int row = m_blk * TC_BM + quarter * 32 + lane;
+            const bool row_ok = row < M;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n0 = n_blk * BN + c0;
+                if (n0 >= N) break;                // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(t_row + c0, r);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                float v[32];
+                const bool full = (n0 + 32 <= N);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                if (epi.bias) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += __ldg(epi.bias + n0 + j);
+                    }
+                }
+                const int64_t o = (int64_t)row * epi.ldc + n0;
+                if (epi.mode == EPI_STORE || epi.mode == EPI_GELU) {
+                    if (epi.mode == EPI_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.C) + o;
+                    if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(cp + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + j < N) cp[j] = __float2bfloat16_rn(v[j]);
+                    }
+                } else {
+                    float* cp = reinterpret_cast<float*>(epi.C) + o;
+                    const bool vec = full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
+                    if (epi.mode == EPI_RESID) {
+                        if (vec) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 c4 = *reinterpret_cast<float4*>(cp + j);
+                                c4.x += v[j]; c4.y += v[j + 1]; c4.z += v[j + 2]; c4.w += v[j + 3];
+                                *reinterpret_cast<float4*>(cp + j) = c4;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n0 + j < N) cp[j] += v[j];
+                        }
+                    } else {
+                        if (epi.mode == EPI_GELU_POS) {
+                            const float* pp = epi.pos + (int64_t)(row % epi.pos_period) * N + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] = gelu_erf(v[j]) + __ldg(pp + j);
+                        }
+                        if (vec) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (n0 + j < N) cp[j] = v[j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_sm_count = 148;
+
+using MapKey = std::tuple<const void*, int64_t, int64_t, int64_t, int>;
+static std::map<MapKey, CUtensorMap> g_maps;     // per process; a ctx is per device per process
+
+int gemm_tc_init(tw_ctx* ctx) {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            ctx->set_error(TW_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+            return TW_E_CUDA;
+        }
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    g_sm_count = ctx->sm_count;
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES));
+    return TW_OK;
+}
+
+static int get_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
+    const MapKey key(ptr, rows, cols, ld, box_rows);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+        *out = it->second;
+        return TW_OK;
+    }
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctx->set_error(TW_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rows=" + std::to_string(rows) +
+                                      " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld));
+        return TW_E_CUDA;
+    }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+    *out = m;
+    return TW_OK;
+}
+
+int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
+            const GemmEpi& epi, cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return TW_OK;
+    if ((lda % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15)) {
+        ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc: operands must be 16-byte aligned with row pitch a multiple of 8 elements");
+        return TW_E_UNSUPPORTED;
+    }
+    // skinny (decode, M <= 128): the GEMM streams W once; narrow N tiles spread it over many SMs
+    const int BN = (M <= TC_BM) ? 32 : ((N > 128) ? 256 : 128);
+    CUtensorMap ma, mw;
+    TW_CHECK(get_map(ctx, A, M, K, lda, TC_BM, &ma));
+    TW_CHECK(get_map(ctx, W, N, K, ldw, BN, &mw));
+    const int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+    if (BN == 256)
+        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+    else if (BN == 32)
+        gemm_tc_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+    else
+        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+}  // namespace tw

@@ -1,0 +1,91 @@
+// Launcher declarations shared by the model orchestration (model.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tw {
+
+// ---- log-mel (logmel.cu)
+int logmel_init(tw_ctx* ctx);
+void logmel_destroy(tw_ctx* ctx);
+int logmel_run(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B, int n_mel,
+               float* out, cudaStream_t st);
+
+// ---- GEMM  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)   (torch Linear layout)
+enum Epi {
+    EPI_STORE = 0,     // C (T)   = acc + bias
+    EPI_GELU = 1,      // C (T)   = gelu(acc + bias)
+    EPI_RESID = 2,     // C (f32) += acc + bias                      (residual stream)
+    EPI_GELU_POS = 3,  // C (f32) = gelu(acc + bias) + pos[row % pos_period]   (conv2 + sinusoids)
+    EPI_F32 = 4,       // C (f32) = acc + bias                      (logits)
+};
+
+struct GemmEpi {
+    int mode = EPI_STORE;
+    const float* bias = nullptr;  // [N] or null
+    void* C = nullptr;
+    int64_t ldc = 0;
+    const float* pos = nullptr;   // [pos_period, N] f32 (EPI_GELU_POS)
+    int pos_period = 1;
+};
+
+// CUDA-core FMA GEMM, fp32 accumulate in a fixed order; the fp32 check-mode path (T = float)
+// and the bring-up / cross-check path for T = bf16.
+template <typename T>
+void gemm_simt(const T* A, int64_t lda, const T* W, int64_t ldw, int M, int N, int K, const GemmEpi& epi, cudaStream_t st);
+
+// tcgen05 / TMEM / TMA GEMM (gemm_tc.cu), bf16 x bf16 -> fp32.  Returns TW_E_UNSUPPORTED when the
+// shape cannot be tiled (caller must not fall back silently: model.cu reports the error).
+int gemm_tc_init(tw_ctx* ctx);
+int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
+            const GemmEpi& epi, cudaStream_t st);
+
+// ---- elementwise / normalisation (elementwise.cu)
+template <typename T>
+void layernorm(const float* x, const float* gamma, const float* beta, T* out, int M, int d, cudaStream_t st);
+// mel f32 [B,n_mel,3000] -> A1 T [B*3000, 3*n_mel], column = tap*n_mel + channel (pad 1)
+template <typename T>
+void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st);
+// h0 T [B*3000, d] -> A2 T [B*1500, 3*d], column = tap*d + channel (stride 2, pad 1)
+template <typename T>
+void im2col_conv2(const T* h0, T* out, int B, int d, cudaStream_t st);
+// x[b] = E[tok[b]] + P[pos]   (f32 residual stream)
+template <typename T>
+void embed_tokens(const int32_t* tok, const T* E, const T* P, int pos, float* x, int B, int d, cudaStream_t st);
+// cache[b][pos][0:2d] = qkv[b][d:3d]
+template <typename T>
+void kv_append(const T* qkv, T* cache, int pos, int B, int d, int max_len, cudaStream_t st);
+void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
+
+// ---- attention (attention.cu)
+// encoder self-attention on qkv T [B*S, 3d] (q pre-scaled), S keys per clip, out T [B*S, d]
+template <typename T>
+void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStream_t st);
+// decode attention (1 query per clip) over kv rows [Tk][2d] (K|V), clip stride kv_clip_stride elements.
+// q T [B, q_stride]; partial workspace f32 [B * nchunks * H * 66]; out T [B, d].
+template <typename T>
+void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial,
+                      T* out, cudaStream_t st);
+int decode_attention_chunks(int Tk);
+
+// ---- token selection (select.cu)
+struct RulesDev {
+    const uint8_t* suppress_mask;        // [V] 1 = always suppressed
+    const uint8_t* begin_suppress_mask;  // [V] 1 = suppressed at the first generated position
+    int eos, pad, ts_begin, no_timestamps, max_initial_ts;
+};
+struct DecodeState {
+    int32_t* cur_tok;     // [B] token fed to the next step
+    int32_t* finished;    // [B]
+    int32_t* n_gen;       // [B] tokens fed back so far (history length)
+    int32_t* last_tok;    // [B] history[-1]
+    int32_t* prev_tok;    // [B] history[-2]
+    int32_t* last_ts;     // [B] most recent timestamp token in the history (or -1)
+    int32_t* n_unfinished;  // [1]
+};
+// one CTA per row: rules -> argmax -> finished/pad bookkeeping -> next input token
+void select_tokens(const float* logits, int V, int B, int gen_index, int out_stride, const RulesDev& rules, const DecodeState& st,
+                   int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream);
+void decode_state_init(const DecodeState& st, int B, int first_tok, cudaStream_t stream);
+void set_cur_tok(const DecodeState& st, int B, int tok, cudaStream_t stream);
+
+}  // namespace tw

@@ -1,0 +1,718 @@
+// Host orchestration of the Whisper teacher-inference path and the C ABI (include/twb200.h).
+// One tw_model = repacked weights + workspace + KV stores for up to max_batch 30 s windows.
+//
+// Call order per batch (what the reference does with feature_extractor(...) + model.generate(...),
+// ref: training/run_pseudo_labelling.py:739,917-918; prefiltering/validator_inference.py:57-60,78):
+//   log-mel (K1) -> conv stem as im2col + GEMM with fused GELU(+positions) -> L_enc x {LN, QKV GEMM,
+//   attention, out-proj GEMM (+residual), LN, fc1 GEMM (+GELU), fc2 GEMM (+residual)} -> LN
+//   -> cross-attention K/V for every decoder layer (once per window) -> greedy loop on the device.
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace tw;
+
+namespace {
+
+// ---- weight repack kernels -----------------------------------------------------------------
+template <typename Dst>
+__global__ void repack_copy_kernel(const void* __restrict__ src, int src_dtype, Dst* __restrict__ dst, int64_t n, float scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = (src_dtype == TW_F32) ? reinterpret_cast<const float*>(src)[i]
+                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+        dst[i] = from_f32<Dst>(v * scale);
+    }
+}
+// conv weight [d_out, C, 3] -> [d_out, 3*C] with column = tap*C + c
+template <typename Dst>
+__global__ void repack_conv_kernel(const void* __restrict__ src, int src_dtype, Dst* __restrict__ dst, int d_out, int C) {
+    const int64_t n = (int64_t)d_out * C * 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % 3);
+        const int c = (int)((i / 3) % C);
+        const int64_t o = i / (3 * (int64_t)C);
+        const float v = (src_dtype == TW_F32) ? reinterpret_cast<const float*>(src)[i]
+                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i]);
+        dst[o * 3 * C + (int64_t)tap * C + c] = from_f32<Dst>(v);
+    }
+}
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void mask_from_ids_kernel(const int32_t* ids, int n, uint8_t* mask, int V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ids[i] >= 0 && ids[i] < V) mask[ids[i]] = 1;
+}
+
+inline int nblocks(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+struct AttnW {
+    void* qkv_w = nullptr;   // [3d, d] (q rows pre-scaled by head_dim^-0.5; exact, 0.125)
+    float* qkv_b = nullptr;  // [3d] (k part zero: k_proj has no bias)
+    void* q_w = nullptr;     // cross-attn: [d, d] scaled
+    float* q_b = nullptr;
+    void* kv_w = nullptr;    // cross-attn: [2d, d] = [Wk; Wv]
+    float* kv_b = nullptr;   // [2d] = [0; bv]
+    void* o_w = nullptr;     // [d, d]
+    float* o_b = nullptr;
+};
+struct LayerW {
+    float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr;
+    AttnW self, cross;
+    void* fc1_w = nullptr;
+    float* fc1_b = nullptr;
+    void* fc2_w = nullptr;
+    float* fc2_b = nullptr;
+};
+
+}  // namespace
+
+struct tw_model {
+    tw_ctx* ctx = nullptr;
+    tw_model_desc desc{};
+    int esz = 2;                 // bytes per element of the model dtype
+    bool use_tc = false;         // tcgen05 GEMMs (bf16 only)
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    // weights
+    void *conv1_w = nullptr, *conv2_w = nullptr;
+    float *conv1_b = nullptr, *conv2_b = nullptr, *enc_pos = nullptr, *enc_lnf_g = nullptr, *enc_lnf_b = nullptr;
+    std::vector<LayerW> enc, dec;
+    void *embed = nullptr, *dec_pos = nullptr;
+    float *dec_lnf_g = nullptr, *dec_lnf_b = nullptr;
+    // workspace
+    int16_t* ws_pcm = nullptr;
+    int32_t* ws_nvalid = nullptr;
+    float* ws_mel = nullptr;
+    void *ws_a1 = nullptr, *ws_h0 = nullptr, *ws_a2qkv = nullptr, *ws_xn = nullptr, *ws_att = nullptr, *ws_hmid = nullptr,
+         *ws_enc = nullptr;
+    float* ws_x = nullptr;
+    void* xkv = nullptr;       // [L_dec][maxB*1500][2d]
+    void* self_kv = nullptr;   // [L_dec][maxB][max_target][2d]
+    float *dx = nullptr, *dlogits = nullptr, *dpartial = nullptr;
+    void *dxn = nullptr, *dqkv = nullptr, *datt = nullptr, *dq = nullptr, *dhmid = nullptr;
+    int32_t* dstate = nullptr;  // 6*maxB + 1 ints
+    uint8_t *d_suppress = nullptr, *d_begin_suppress = nullptr;
+    int32_t* d_ids_tmp = nullptr;
+    int32_t *d_out_tok = nullptr, *d_out_len = nullptr;
+    int32_t* h_flag = nullptr;   // pinned
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    bool ev_valid[6] = {false, false, false, false, false, false};
+};
+
+namespace {
+
+int dev_alloc(tw_model* m, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        m->ctx->set_error(TW_E_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        return TW_E_NOMEM;
+    }
+    m->allocs.push_back(*p);
+    m->bytes += bytes;
+    return TW_OK;
+}
+
+struct WeightTable {
+    std::map<std::string, const tw_weight*> by_name;
+    const tw_weight* get(tw_ctx* ctx, const std::string& name, int64_t numel) const {
+        auto it = by_name.find(name);
+        if (it == by_name.end()) {
+            ctx->set_error(TW_E_INVALID, "tw_model_load: missing weight " + name);
+            return nullptr;
+        }
+        if (it->second->numel != numel) {
+            ctx->set_error(TW_E_SHAPE, "tw_model_load: weight " + name + " has " + std::to_string(it->second->numel) +
+                                           " elements, expected " + std::to_string(numel));
+            return nullptr;
+        }
+        if (it->second->dtype != TW_F32 && it->second->dtype != TW_BF16) {
+            ctx->set_error(TW_E_INVALID, "tw_model_load: weight " + name + " must be float32 or bfloat16");
+            return nullptr;
+        }
+        return it->second;
+    }
+};
+
+template <typename T>
+int put(tw_model* m, const WeightTable& wt, const std::string& name, int64_t numel, T* dst, float scale = 1.0f) {
+    const tw_weight* w = wt.get(m->ctx, name, numel);
+    if (!w) return m->ctx->err_code;
+    repack_copy_kernel<T><<<nblocks(numel), 256>>>(w->ptr, w->dtype, dst, numel, scale);
+    return TW_OK;
+}
+
+template <typename T>
+int load_attn(tw_model* m, const WeightTable& wt, const std::string& pre, AttnW& a, bool cross) {
+    const int d = m->desc.d_model;
+    const int64_t dd = (int64_t)d * d;
+    const float qs = 0.125f;    // head_dim 64 -> 64^-0.5, a power of two: folding it into Wq/bq is exact
+    if (!cross) {
+        TW_CHECK(dev_alloc(m, &a.qkv_w, 3 * dd * sizeof(T)));
+        TW_CHECK(dev_alloc(m, (void**)&a.qkv_b, 3 * d * sizeof(float)));
+        fill_f32_kernel<<<nblocks(3 * d), 256>>>(a.qkv_b, 3 * d, 0.0f);
+        T* w = (T*)a.qkv_w;
+        TW_CHECK(put<T>(m, wt, pre + "q_proj.weight", dd, w, qs));
+        TW_CHECK(put<T>(m, wt, pre + "k_proj.weight", dd, w + dd));
+        TW_CHECK(put<T>(m, wt, pre + "v_proj.weight", dd, w + 2 * dd));
+        TW_CHECK(put<float>(m, wt, pre + "q_proj.bias", d, a.qkv_b, qs));
+        TW_CHECK(put<float>(m, wt, pre + "v_proj.bias", d, a.qkv_b + 2 * d));
+    } else {
+        TW_CHECK(dev_alloc(m, &a.q_w, dd * sizeof(T)));
+        TW_CHECK(dev_alloc(m, (void**)&a.q_b, d * sizeof(float)));
+        TW_CHECK(dev_alloc(m, &a.kv_w, 2 * dd * sizeof(T)));
+        TW_CHECK(dev_alloc(m, (void**)&a.kv_b, 2 * d * sizeof(float)));
+        fill_f32_kernel<<<nblocks(2 * d), 256>>>(a.kv_b, 2 * d, 0.0f);
+        TW_CHECK(put<T>(m, wt, pre + "q_proj.weight", dd, (T*)a.q_w, qs));
+        TW_CHECK(put<float>(m, wt, pre + "q_proj.bias", d, a.q_b, qs));
+        TW_CHECK(put<T>(m, wt, pre + "k_proj.weight", dd, (T*)a.kv_w));
+        TW_CHECK(put<T>(m, wt, pre + "v_proj.weight", dd, (T*)a.kv_w + dd));
+        TW_CHECK(put<float>(m, wt, pre + "v_proj.bias", d, a.kv_b + d));
+    }
+    TW_CHECK(dev_alloc(m, &a.o_w, dd * sizeof(T)));
+    TW_CHECK(dev_alloc(m, (void**)&a.o_b, d * sizeof(float)));
+    TW_CHECK(put<T>(m, wt, pre + "out_proj.weight", dd, (T*)a.o_w));
+    TW_CHECK(put<float>(m, wt, pre + "out_proj.bias", d, a.o_b));
+    return TW_OK;
+}
+
+int load_ln(tw_model* m, const WeightTable& wt, const std::string& pre, float** g, float** b) {
+    const int d = m->desc.d_model;
+    TW_CHECK(dev_alloc(m, (void**)g, d * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)b, d * sizeof(float)));
+    TW_CHECK(put<float>(m, wt, pre + ".weight", d, *g));
+    TW_CHECK(put<float>(m, wt, pre + ".bias", d, *b));
+    return TW_OK;
+}
+
+template <typename T>
+int load_mlp(tw_model* m, const WeightTable& wt, const std::string& pre, LayerW& L) {
+    const int d = m->desc.d_model, f = m->desc.ffn;
+    TW_CHECK(dev_alloc(m, &L.fc1_w, (size_t)f * d * sizeof(T)));
+    TW_CHECK(dev_alloc(m, (void**)&L.fc1_b, f * sizeof(float)));
+    TW_CHECK(dev_alloc(m, &L.fc2_w, (size_t)f * d * sizeof(T)));
+    TW_CHECK(dev_alloc(m, (void**)&L.fc2_b, d * sizeof(float)));
+    TW_CHECK(put<T>(m, wt, pre + "fc1.weight", (int64_t)f * d, (T*)L.fc1_w));
+    TW_CHECK(put<float>(m, wt, pre + "fc1.bias", f, L.fc1_b));
+    TW_CHECK(put<T>(m, wt, pre + "fc2.weight", (int64_t)f * d, (T*)L.fc2_w));
+    TW_CHECK(put<float>(m, wt, pre + "fc2.bias", d, L.fc2_b));
+    return TW_OK;
+}
+
+template <typename T>
+int load_weights(tw_model* m, const WeightTable& wt) {
+    const tw_model_desc& D = m->desc;
+    const int d = D.d_model;
+    const std::string E = "model.encoder.", Dc = "model.decoder.";
+    // conv stem
+    TW_CHECK(dev_alloc(m, &m->conv1_w, (size_t)d * 3 * D.n_mel * sizeof(T)));
+    TW_CHECK(dev_alloc(m, &m->conv2_w, (size_t)d * 3 * d * sizeof(T)));
+    TW_CHECK(dev_alloc(m, (void**)&m->conv1_b, d * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)&m->conv2_b, d * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)&m->enc_pos, (size_t)TW_N_CTX * d * sizeof(float)));
+    {
+        const tw_weight* w1 = wt.get(m->ctx, E + "conv1.weight", (int64_t)d * D.n_mel * 3);
+        const tw_weight* w2 = wt.get(m->ctx, E + "conv2.weight", (int64_t)d * d * 3);
+        if (!w1 || !w2) return m->ctx->err_code;
+        repack_conv_kernel<T><<<nblocks((int64_t)d * D.n_mel * 3), 256>>>(w1->ptr, w1->dtype, (T*)m->conv1_w, d, D.n_mel);
+        repack_conv_kernel<T><<<nblocks((int64_t)d * d * 3), 256>>>(w2->ptr, w2->dtype, (T*)m->conv2_w, d, d);
+    }
+    TW_CHECK(put<float>(m, wt, E + "conv1.bias", d, m->conv1_b));
+    TW_CHECK(put<float>(m, wt, E + "conv2.bias", d, m->conv2_b));
+    TW_CHECK(put<float>(m, wt, E + "embed_positions.weight", (int64_t)TW_N_CTX * d, m->enc_pos));
+    m->enc.resize(D.enc_layers);
+    for (int l = 0; l < D.enc_layers; ++l) {
+        const std::string p = E + "layers." + std::to_string(l) + ".";
+        LayerW& L = m->enc[l];
+        TW_CHECK(load_ln(m, wt, p + "self_attn_layer_norm", &L.ln1_g, &L.ln1_b));
+        TW_CHECK(load_attn<T>(m, wt, p + "self_attn.", L.self, false));
+        TW_CHECK(load_ln(m, wt, p + "final_layer_norm", &L.ln3_g, &L.ln3_b));
+        TW_CHECK(load_mlp<T>(m, wt, p, L));
+    }
+    TW_CHECK(load_ln(m, wt, E + "layer_norm", &m->enc_lnf_g, &m->enc_lnf_b));
+    // decoder
+    TW_CHECK(dev_alloc(m, &m->embed, (size_t)D.vocab * d * sizeof(T)));
+    TW_CHECK(dev_alloc(m, &m->dec_pos, (size_t)D.max_target * d * sizeof(T)));
+    TW_CHECK(put<T>(m, wt, Dc + "embed_tokens.weight", (int64_t)D.vocab * d, (T*)m->embed));
+    TW_CHECK(put<T>(m, wt, Dc + "embed_positions.weight", (int64_t)D.max_target * d, (T*)m->dec_pos));
+    m->dec.resize(D.dec_layers);
+    for (int l = 0; l < D.dec_layers; ++l) {
+        const std::string p = Dc + "layers." + std::to_string(l) + ".";
+        LayerW& L = m->dec[l];
+        TW_CHECK(load_ln(m, wt, p + "self_attn_layer_norm", &L.ln1_g, &L.ln1_b));
+        TW_CHECK(load_attn<T>(m, wt, p + "self_attn.", L.self, false));
+        TW_CHECK(load_ln(m, wt, p + "encoder_attn_layer_norm", &L.ln2_g, &L.ln2_b));
+        TW_CHECK(load_attn<T>(m, wt, p + "encoder_attn.", L.cross, true));
+        TW_CHECK(load_ln(m, wt, p + "final_layer_norm", &L.ln3_g, &L.ln3_b));
+        TW_CHECK(load_mlp<T>(m, wt, p, L));
+    }
+    TW_CHECK(load_ln(m, wt, Dc + "layer_norm", &m->dec_lnf_g, &m->dec_lnf_b));
+    TW_CUDA_OK(m->ctx, cudaDeviceSynchronize());
+    TW_CUDA_OK(m->ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int alloc_workspace(tw_model* m) {
+    const tw_model_desc& D = m->desc;
+    const size_t B = D.max_batch, d = D.d_model, e = m->esz;
+    const size_t M = B * TW_N_CTX;
+    TW_CHECK(dev_alloc(m, (void**)&m->ws_pcm, B * TW_N_SAMPLES * sizeof(int16_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->ws_nvalid, B * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->ws_mel, B * D.n_mel * TW_N_FRAMES * sizeof(float)));
+    TW_CHECK(dev_alloc(m, &m->ws_a1, B * TW_N_FRAMES * 3 * D.n_mel * e));
+    TW_CHECK(dev_alloc(m, &m->ws_h0, B * TW_N_FRAMES * d * e));
+    TW_CHECK(dev_alloc(m, &m->ws_a2qkv, M * 3 * d * e));
+    TW_CHECK(dev_alloc(m, (void**)&m->ws_x, M * d * sizeof(float)));
+    TW_CHECK(dev_alloc(m, &m->ws_xn, M * d * e));
+    TW_CHECK(dev_alloc(m, &m->ws_att, M * d * e));
+    TW_CHECK(dev_alloc(m, &m->ws_hmid, M * D.ffn * e));
+    TW_CHECK(dev_alloc(m, &m->ws_enc, M * d * e));
+    TW_CHECK(dev_alloc(m, &m->xkv, (size_t)D.dec_layers * M * 2 * d * e));
+    TW_CHECK(dev_alloc(m, &m->self_kv, (size_t)D.dec_layers * B * D.max_target * 2 * d * e));
+    TW_CHECK(dev_alloc(m, (void**)&m->dx, B * d * sizeof(float)));
+    TW_CHECK(dev_alloc(m, &m->dxn, B * d * e));
+    TW_CHECK(dev_alloc(m, &m->dqkv, B * 3 * d * e));
+    TW_CHECK(dev_alloc(m, &m->datt, B * d * e));
+    TW_CHECK(dev_alloc(m, &m->dq, B * d * e));
+    TW_CHECK(dev_alloc(m, &m->dhmid, B * D.ffn * e));
+    TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * D.vocab * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)&m->dpartial, B * decode_attention_chunks(TW_N_CTX) * D.heads * 66 * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)&m->dstate, (6 * B + 4) * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_ids_tmp, 4096 * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_out_tok, B * D.max_target * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_out_len, B * sizeof(int32_t)));
+    for (auto& ev : m->ev) TW_CUDA_OK(m->ctx, cudaEventCreate(&ev));
+    TW_CUDA_OK(m->ctx, cudaMallocHost(&m->h_flag, 64));
+    return TW_OK;
+}
+
+// ---- GEMM dispatch: tcgen05 for bf16 (unless TWB200_GEMM=simt), CUDA-core FMA for the fp32 check mode
+template <typename T>
+int gemm(tw_model* m, const T* A, int64_t lda, const T* W, int64_t ldw, int M, int N, int K, const GemmEpi& epi, cudaStream_t st);
+
+template <>
+int gemm<float>(tw_model* m, const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K, const GemmEpi& epi,
+                cudaStream_t st) {
+    gemm_simt<float>(A, lda, W, ldw, M, N, K, epi, st);
+    m->ctx->launches += 1;
+    return TW_OK;
+}
+template <>
+int gemm<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
+                        const GemmEpi& epi, cudaStream_t st) {
+    m->ctx->launches += 1;
+    if (m->use_tc) return gemm_tc(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
+    gemm_simt<__nv_bfloat16>(A, lda, W, ldw, M, N, K, epi, st);
+    return TW_OK;
+}
+
+inline GemmEpi mk_epi(int mode, const float* bias, void* C, int64_t ldc, const float* pos = nullptr, int period = 1) {
+    GemmEpi e;
+    e.mode = mode; e.bias = bias; e.C = C; e.ldc = ldc; e.pos = pos; e.pos_period = period;
+    return e;
+}
+
+template <typename T>
+int encode_impl(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, cudaStream_t st) {
+    const tw_model_desc& D = m->desc;
+    const int d = D.d_model, M = B * TW_N_CTX, M0 = B * TW_N_FRAMES, K1 = 3 * D.n_mel;
+    tw_ctx* ctx = m->ctx;
+    T* a1 = (T*)m->ws_a1; T* h0 = (T*)m->ws_h0; T* a2 = (T*)m->ws_a2qkv; T* qkv = (T*)m->ws_a2qkv;
+    T* xn = (T*)m->ws_xn; T* att = (T*)m->ws_att; T* hmid = (T*)m->ws_hmid;
+    float* x = m->ws_x;
+    im2col_conv1<T>(mel, a1, B, D.n_mel, st);
+    TW_CHECK(gemm<T>(m, a1, K1, (const T*)m->conv1_w, K1, M0, d, K1, mk_epi(EPI_GELU, m->conv1_b, h0, d), st));
+    im2col_conv2<T>(h0, a2, B, d, st);
+    TW_CHECK(gemm<T>(m, a2, 3 * d, (const T*)m->conv2_w, 3 * d, M, d, 3 * d,
+                     mk_epi(EPI_GELU_POS, m->conv2_b, x, d, m->enc_pos, TW_N_CTX), st));
+    ctx->launches += 2;
+    if (tap_layer == 0 && tap_out) { copy_f32(x, tap_out, (int64_t)M * d, st); ctx->launches += 1; }
+    for (int l = 0; l < D.enc_layers; ++l) {
+        const LayerW& L = m->enc[l];
+        layernorm<T>(x, L.ln1_g, L.ln1_b, xn, M, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, M, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
+        encoder_attention_simt<T>(qkv, att, B, TW_N_CTX, D.heads, st);
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, M, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+        layernorm<T>(x, L.ln3_g, L.ln3_b, xn, M, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, M, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+        TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, M, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+        ctx->launches += 3;
+        if (tap_layer == l + 1 && tap_out) { copy_f32(x, tap_out, (int64_t)M * d, st); ctx->launches += 1; }
+    }
+    layernorm<T>(x, m->enc_lnf_g, m->enc_lnf_b, (T*)enc_out, M, d, st);
+    ctx->launches += 1;
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+template <typename T>
+int cross_kv_impl(tw_model* m, const void* enc_out, int B, cudaStream_t st) {
+    const tw_model_desc& D = m->desc;
+    const int d = D.d_model, M = B * TW_N_CTX;
+    for (int l = 0; l < D.dec_layers; ++l) {
+        T* dst = (T*)m->xkv + (size_t)l * D.max_batch * TW_N_CTX * 2 * d;
+        TW_CHECK(gemm<T>(m, (const T*)enc_out, d, (const T*)m->dec[l].cross.kv_w, d, M, 2 * d, d,
+                         mk_epi(EPI_STORE, m->dec[l].cross.kv_b, dst, 2 * d), st));
+    }
+    TW_CUDA_OK(m->ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int upload_rules(tw_model* m, const tw_rules* R, RulesDev* out, cudaStream_t st) {
+    tw_ctx* ctx = m->ctx;
+    const int V = m->desc.vocab;
+    if (R->n_suppress < 0 || R->n_begin_suppress < 0 || R->n_suppress + R->n_begin_suppress > 4096) {
+        ctx->set_error(TW_E_INVALID, "tw_rules: too many suppress ids");
+        return TW_E_INVALID;
+    }
+    TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_suppress, 0, V, st));
+    TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_begin_suppress, 0, V, st));
+    if (R->n_suppress > 0) {
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(m->d_ids_tmp, R->suppress, R->n_suppress * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        mask_from_ids_kernel<<<ceil_div(R->n_suppress, 256), 256, 0, st>>>(m->d_ids_tmp, R->n_suppress, m->d_suppress, V);
+    }
+    if (R->n_begin_suppress > 0) {
+        int32_t* tmp = m->d_ids_tmp + R->n_suppress;
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(tmp, R->begin_suppress, R->n_begin_suppress * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        mask_from_ids_kernel<<<ceil_div(R->n_begin_suppress, 256), 256, 0, st>>>(tmp, R->n_begin_suppress, m->d_begin_suppress, V);
+    }
+    // the host arrays may be pageable: make sure the copies are done before the caller reuses them
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    out->suppress_mask = m->d_suppress;
+    out->begin_suppress_mask = m->d_begin_suppress;
+    out->eos = R->eos;
+    out->pad = R->pad;
+    out->ts_begin = R->timestamp_begin;
+    out->no_timestamps = R->no_timestamps;
+    out->max_initial_ts = R->max_initial_timestamp_index;
+    return TW_OK;
+}
+
+template <typename T>
+int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev& R, int max_length, int32_t* out_tokens,
+                int32_t* out_lengths, const int32_t* forced, float* logits_tap, int tap_steps, cudaStream_t st) {
+    const tw_model_desc& D = m->desc;
+    tw_ctx* ctx = m->ctx;
+    const int d = D.d_model, V = D.vocab, H = D.heads;
+    const int n_gen_max = max_length - P;
+    DecodeState S;
+    S.cur_tok = m->dstate;
+    S.finished = m->dstate + D.max_batch;
+    S.n_gen = m->dstate + 2 * D.max_batch;
+    S.last_tok = m->dstate + 3 * D.max_batch;
+    S.prev_tok = m->dstate + 4 * D.max_batch;
+    S.last_ts = m->dstate + 5 * D.max_batch;
+    S.n_unfinished = m->dstate + 6 * D.max_batch;
+    decode_state_init(S, B, prompt[0], st);
+    TW_CUDA_OK(ctx, cudaMemsetAsync(out_lengths, 0, B * sizeof(int32_t), st));
+    float* x = m->dx;
+    T* xn = (T*)m->dxn; T* qkv = (T*)m->dqkv; T* att = (T*)m->datt; T* q = (T*)m->dq; T* hmid = (T*)m->dhmid;
+    const size_t self_layer = (size_t)D.max_batch * D.max_target * 2 * d;
+    const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
+    int32_t* h_unfinished = m->h_flag;
+    *h_unfinished = B;
+    bool check_pending = false;
+    // positions 0..P-1 consume the forced prompt (prefill as P single-token steps), then one step per token
+    for (int pos = 0; pos < max_length - 1; ++pos) {
+        embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, pos, x, B, d, st);
+        for (int l = 0; l < D.dec_layers; ++l) {
+            const LayerW& L = m->dec[l];
+            T* cache = (T*)m->self_kv + l * self_layer;
+            layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
+            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
+            kv_append<T>(qkv, cache, pos, B, d, D.max_target, st);
+            decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, pos + 1, B, H, m->dpartial, att, st);
+            TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+            layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
+            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+            decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, B, H, m->dpartial, att,
+                                st);
+            TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
+            layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
+            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+            TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+            ctx->launches += 8;
+        }
+        ctx->launches += 1;
+        if (pos < P - 1) {
+            set_cur_tok(S, B, prompt[pos + 1], st);      // still inside the forced prompt
+            ctx->launches += 1;
+            continue;
+        }
+        const int g = pos - (P - 1);                     // index of the token being generated
+        layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
+        float* tap = (logits_tap && g < tap_steps) ? logits_tap + (size_t)g * B * V : nullptr;
+        select_tokens(m->dlogits, V, B, g, n_gen_max, R, S, out_tokens, out_lengths, forced, tap, st);
+        ctx->launches += 2;
+        // early exit when every row has emitted EOS: the count is copied back every 8 tokens and read 8
+        // tokens later, so the launch queue never drains (random-init models never emit EOS)
+        if ((g & 7) == 7) {
+            bool all_done = false;
+            if (check_pending) {
+                TW_CUDA_OK(ctx, cudaEventSynchronize(m->ev[5]));
+                all_done = (*h_unfinished <= 0);
+            }
+            if (!all_done) {
+                TW_CUDA_OK(ctx, cudaMemcpyAsync(h_unfinished, S.n_unfinished, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                TW_CUDA_OK(ctx, cudaEventRecord(m->ev[5], st));
+                check_pending = true;
+            }
+            if (all_done) {
+                // remaining positions: pad
+                for (int g2 = g + 1; g2 < n_gen_max; ++g2) {
+                    select_tokens(m->dlogits, V, B, g2, n_gen_max, R, S, out_tokens, out_lengths, forced, nullptr, st);
+                    ctx->launches += 1;
+                }
+                break;
+            }
+        }
+    }
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+bool check_model(tw_model* m, const char* fn) {
+    return m && m->ctx && fn;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+extern "C" {
+
+int tw_abi_version(void) { return TWB200_ABI_VERSION; }
+
+int tw_ctx_create(int device, tw_ctx** out) {
+    if (!out) return TW_E_INVALID;
+    *out = nullptr;
+    tw_ctx* ctx = new (std::nothrow) tw_ctx();
+    if (!ctx) return TW_E_NOMEM;
+    ctx->device = device;
+    *out = ctx;        // returned even on failure so that tw_last_error can be read
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        ctx->set_error(TW_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                      " (libtwb200 has no CPU fallback)");
+        return TW_E_CUDA;
+    }
+    TW_CUDA_OK(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TW_CUDA_OK(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        ctx->set_error(TW_E_UNSUPPORTED, "libtwb200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) +
+                                             std::to_string(prop.minor));
+        return TW_E_UNSUPPORTED;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    TW_CHECK(logmel_init(ctx));
+    TW_CHECK(gemm_tc_init(ctx));
+    return TW_OK;
+}
+
+void tw_ctx_destroy(tw_ctx* ctx) {
+    if (!ctx) return;
+    logmel_destroy(ctx);
+    delete ctx;
+}
+
+const char* tw_last_error(const tw_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+uint64_t tw_launch_count(const tw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int tw_logmel(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B, int n_mel, float* out,
+              void* stream) {
+    if (!ctx) return TW_E_INVALID;
+    if (B < 0) { ctx->set_error(TW_E_INVALID, "tw_logmel: B < 0"); return TW_E_INVALID; }
+    return logmel_run(ctx, pcm, pcm_dtype, pcm_stride, n_valid, B, n_mel, out, (cudaStream_t)stream);
+}
+
+int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table, size_t n, tw_model** out) {
+    if (!ctx || !desc || !table || !out) return TW_E_INVALID;
+    *out = nullptr;
+    const tw_model_desc& D = *desc;
+    if (D.d_model <= 0 || D.heads <= 0 || D.d_model != D.heads * 64 || D.d_model > 1280 || D.d_model % 8 != 0) {
+        ctx->set_error(TW_E_INVALID, "tw_model_load: d_model must be heads*64 and <= 1280");
+        return TW_E_INVALID;
+    }
+    if ((D.n_mel != 80 && D.n_mel != 128) || D.ffn <= 0 || D.ffn % 8 != 0 || D.enc_layers <= 0 || D.dec_layers <= 0 || D.vocab <= 0 ||
+        D.max_target <= 1 || D.max_batch <= 0 || (D.dtype != TW_BF16 && D.dtype != TW_F32)) {
+        ctx->set_error(TW_E_INVALID, "tw_model_load: bad model descriptor");
+        return TW_E_INVALID;
+    }
+    tw_model* m = new (std::nothrow) tw_model();
+    if (!m) return TW_E_NOMEM;
+    m->ctx = ctx;
+    m->desc = D;
+    m->esz = D.dtype == TW_BF16 ? 2 : 4;
+    const char* g = getenv("TWB200_GEMM");
+    m->use_tc = (D.dtype == TW_BF16) && !(g && strcmp(g, "simt") == 0);
+    WeightTable wt;
+    for (size_t i = 0; i < n; ++i)
+        if (table[i].name) wt.by_name[table[i].name] = &table[i];
+    int r = (D.dtype == TW_BF16) ? load_weights<__nv_bfloat16>(m, wt) : load_weights<float>(m, wt);
+    if (r == TW_OK) r = alloc_workspace(m);
+    if (r != TW_OK) {
+        tw_model_free(m);
+        return r;
+    }
+    *out = m;
+    return TW_OK;
+}
+
+void tw_model_free(tw_model* m) {
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->h_flag) cudaFreeHost(m->h_flag);
+    for (auto& ev : m->ev)
+        if (ev) cudaEventDestroy(ev);
+    delete m;
+}
+
+size_t tw_model_bytes(const tw_model* m) { return m ? m->bytes : 0; }
+
+int tw_encode(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, void* stream) {
+    if (!check_model(m, "tw_encode")) return TW_E_INVALID;
+    if (B <= 0 || B > m->desc.max_batch || !mel || !enc_out) {
+        m->ctx->set_error(TW_E_INVALID, "tw_encode: bad batch (1..max_batch) or null buffer");
+        return TW_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    return m->desc.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, mel, B, enc_out, tap_layer, tap_out, st)
+                                    : encode_impl<float>(m, mel, B, enc_out, tap_layer, tap_out, st);
+}
+
+static int check_decode_args(tw_model* m, int B, const int32_t* prompt, int P, const tw_rules* rules, int max_length) {
+    tw_ctx* ctx = m->ctx;
+    if (B <= 0 || B > m->desc.max_batch || !prompt || !rules) {
+        ctx->set_error(TW_E_INVALID, "decode: bad batch or null argument");
+        return TW_E_INVALID;
+    }
+    if (P < 1 || max_length <= P || max_length > m->desc.max_target) {
+        // HF raises ValueError when prompt + new tokens exceed max_target_positions (generation_whisper.py:1922-1931)
+        ctx->set_error(TW_E_INVALID, "decode: need 1 <= P < max_length <= max_target_positions (" +
+                                         std::to_string(m->desc.max_target) + ")");
+        return TW_E_INVALID;
+    }
+    for (int i = 0; i < P; ++i)
+        if (prompt[i] < 0 || prompt[i] >= m->desc.vocab) {
+            ctx->set_error(TW_E_INVALID, "decode: prompt token out of range");
+            return TW_E_INVALID;
+        }
+    return TW_OK;
+}
+
+int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* prompt, int P, const tw_rules* rules, int max_length,
+                     int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, int tap_steps,
+                     void* stream) {
+    if (!check_model(m, "tw_decode_greedy")) return TW_E_INVALID;
+    TW_CHECK(check_decode_args(m, B, prompt, P, rules, max_length));
+    if (!enc_out || !out_tokens || !out_lengths) {
+        m->ctx->set_error(TW_E_INVALID, "tw_decode_greedy: null buffer");
+        return TW_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RulesDev R;
+    TW_CHECK(upload_rules(m, rules, &R, st));
+    cudaEventRecord(m->ev[2], st);
+    int r = m->desc.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, enc_out, B, st) : cross_kv_impl<float>(m, enc_out, B, st);
+    if (r != TW_OK) return r;
+    cudaEventRecord(m->ev[3], st);
+    r = m->desc.dtype == TW_BF16
+            ? decode_impl<__nv_bfloat16>(m, B, prompt, P, R, max_length, out_tokens, out_lengths, forced, logits_tap, tap_steps, st)
+            : decode_impl<float>(m, B, prompt, P, R, max_length, out_tokens, out_lengths, forced, logits_tap, tap_steps, st);
+    cudaEventRecord(m->ev[4], st);
+    m->ev_valid[2] = m->ev_valid[3] = m->ev_valid[4] = true;
+    m->ev_valid[0] = m->ev_valid[1] = false;
+    return r;
+}
+
+int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_valid_host, int B, const int32_t* prompt, int P,
+                       const tw_rules* rules, int max_length, int32_t* out_tokens_host, int32_t* out_lengths_host, void* stream) {
+    if (!check_model(m, "tw_transcribe_host")) return TW_E_INVALID;
+    TW_CHECK(check_decode_args(m, B, prompt, P, rules, max_length));
+    if (!pcm_host || !out_tokens_host || !out_lengths_host) {
+        m->ctx->set_error(TW_E_INVALID, "tw_transcribe_host: null buffer");
+        return TW_E_INVALID;
+    }
+    tw_ctx* ctx = m->ctx;
+    cudaStream_t st = (cudaStream_t)stream;
+    const tw_model_desc& D = m->desc;
+    const int n_gen = max_length - P;
+    RulesDev R;
+    TW_CHECK(upload_rules(m, rules, &R, st));
+    cudaEventRecord(m->ev[0], st);
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(m->ws_pcm, pcm_host, (size_t)B * TW_N_SAMPLES * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    const int32_t* nv = nullptr;
+    if (n_valid_host) {
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(m->ws_nvalid, n_valid_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        nv = m->ws_nvalid;
+    }
+    TW_CHECK(logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st));
+    cudaEventRecord(m->ev[1], st);
+    int r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st)
+                               : encode_impl<float>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st);
+    if (r != TW_OK) return r;
+    cudaEventRecord(m->ev[2], st);
+    r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, m->ws_enc, B, st) : cross_kv_impl<float>(m, m->ws_enc, B, st);
+    if (r != TW_OK) return r;
+    cudaEventRecord(m->ev[3], st);
+    r = D.dtype == TW_BF16
+            ? decode_impl<__nv_bfloat16>(m, B, prompt, P, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st)
+            : decode_impl<float>(m, B, prompt, P, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st);
+    if (r != TW_OK) return r;
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(out_tokens_host, m->d_out_tok, (size_t)B * n_gen * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(out_lengths_host, m->d_out_len, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(m->ev[4], st);
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < 5; ++i) m->ev_valid[i] = true;
+    return TW_OK;
+}
+
+int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype, int epi_mode,
+                  const float* pos, int pos_period, int use_tc, void* stream) {
+    if (!ctx || !A || !W || !C) return TW_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    GemmEpi e = mk_epi(epi_mode, bias, C, N, pos, pos_period > 0 ? pos_period : 1);
+    ctx->launches += 1;
+    if (dtype == TW_F32) {
+        gemm_simt<float>((const float*)A, K, (const float*)W, K, M, N, K, e, st);
+    } else if (dtype == TW_BF16) {
+        if (use_tc) return gemm_tc(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
+        gemm_simt<__nv_bfloat16>((const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
+    } else {
+        ctx->set_error(TW_E_INVALID, "tw_debug_gemm: dtype");
+        return TW_E_INVALID;
+    }
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_last_stage_ms(tw_model* m, float out_ms[5]) {
+    if (!m || !out_ms) return TW_E_INVALID;
+    for (int i = 0; i < 5; ++i) out_ms[i] = 0.0f;
+    for (int i = 0; i < 4; ++i)
+        if (m->ev_valid[i] && m->ev_valid[i + 1]) {
+            if (cudaEventSynchronize(m->ev[i + 1]) == cudaSuccess) cudaEventElapsedTime(&out_ms[i], m->ev[i], m->ev[i + 1]);
+        }
+    int first = -1;
+    for (int i = 0; i < 5; ++i)
+        if (m->ev_valid[i]) { first = i; break; }
+    if (first >= 0 && first < 4 && m->ev_valid[4]) cudaEventElapsedTime(&out_ms[4], m->ev[first], m->ev[4]);
+    return TW_OK;
+}
+
+}  // extern "C"

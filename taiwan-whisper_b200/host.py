@@ -1,0 +1,469 @@
+"""Python host of the B200 path: the reference's two call sites, backed by libtwb200 (C ABI).
+
+    fe    = B200WhisperFeatureExtractor(feature_size=128)                # WhisperFeatureExtractor
+    model = B200WhisperForConditionalGeneration.from_hf(hf_model, dtype=torch.bfloat16)
+    feats = fe(list_of_waveforms, sampling_rate=16000, return_tensors="pt", device="cuda")
+    ids   = model.generate(feats["input_features"], max_length=256, num_beams=1,
+                           return_timestamps=False, language="zh", task="transcribe")
+
+mirrors, argument for argument and error for error,
+  ref: training/run_pseudo_labelling.py:739-741 (fe call), :370-374 (fe.pad), :864-876,917-918 (generate)
+  ref: prefiltering/validator_inference.py:41-47,57-69,78
+torch supplies device memory, streams and (in bench.py) torch.distributed only; every FLOP of
+the path runs in the library's CUDA kernels and the ops raise if the library is missing.
+Three `torch.ops.twb200.*` operators expose the same entry points to graph-level callers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .configs import N_FRAMES, N_SAMPLES, SAMPLING_RATE
+
+_TORCH2TW = {torch.float32: _lib.TW_F32, torch.bfloat16: _lib.TW_BF16, torch.int16: _lib.TW_I16, torch.int32: _lib.TW_I32}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dev_index(device) -> int:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise ValueError("twb200 runs on CUDA (B200) devices only; there is no CPU fallback")
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+# --------------------------------------------------------------------------------------------
+# functional layer (device tensors in, device tensors out) — also registered as torch.ops.twb200.*
+def log_mel(pcm: torch.Tensor, n_valid: Optional[torch.Tensor], n_mel: int) -> torch.Tensor:
+    """pcm [B, N] int16 | float32 (cuda) -> [B, n_mel, 3000] float32.  N need not be 480000: rows are
+    zero-extended / truncated to 30 s inside the kernel (HF __call__ pad/trim)."""
+    if pcm.dim() != 2 or pcm.dtype not in (torch.int16, torch.float32):
+        raise ValueError("log_mel expects a [B, N] int16 or float32 tensor")
+    dev = _dev_index(pcm.device)
+    ctx = _lib.Context.get(dev)
+    pcm = pcm.contiguous()
+    B = pcm.shape[0]
+    out = torch.empty((B, n_mel, N_FRAMES), dtype=torch.float32, device=pcm.device)
+    nv_ptr = None
+    if n_valid is not None:
+        n_valid = n_valid.to(device=pcm.device, dtype=torch.int32).contiguous()
+        nv_ptr = n_valid.data_ptr()
+    with torch.cuda.device(dev):
+        ctx.check(ctx.lib.tw_logmel(ctx.handle, pcm.data_ptr(), _TORCH2TW[pcm.dtype], pcm.shape[1], nv_ptr, B, n_mel,
+                                    out.data_ptr(), _stream_ptr(pcm.device)))
+    return out
+
+
+def _register_torch_ops():
+    """torch.ops.twb200.{log_mel, encoder_forward, greedy_generate}: thin operator wrappers over the
+    C ABI (CUDA tensors only, current stream)."""
+    try:
+        from torch.library import custom_op
+    except Exception:  # pragma: no cover
+        return
+
+    @custom_op("twb200::log_mel", mutates_args=())
+    def _op_log_mel(pcm: torch.Tensor, n_mel: int) -> torch.Tensor:
+        return log_mel(pcm, None, n_mel)
+
+    @_op_log_mel.register_fake
+    def _(pcm, n_mel):
+        return pcm.new_empty((pcm.shape[0], n_mel, N_FRAMES), dtype=torch.float32)
+
+    @custom_op("twb200::encoder_forward", mutates_args=())
+    def _op_encoder_forward(handle: int, mel: torch.Tensor) -> torch.Tensor:
+        return _MODELS[handle].encode(mel)
+
+    @_op_encoder_forward.register_fake
+    def _(handle, mel):
+        m = _MODELS[handle]
+        return mel.new_empty((mel.shape[0], 1500, m.shape.d_model), dtype=m.dtype)
+
+    @custom_op("twb200::greedy_generate", mutates_args=())
+    def _op_greedy_generate(handle: int, enc_out: torch.Tensor, prompt: Sequence[int], max_length: int,
+                            timestamps: bool) -> torch.Tensor:
+        toks, lens = _MODELS[handle].decode(enc_out, list(prompt), max_length, timestamps)
+        return torch.cat([toks, lens[:, None]], dim=1)
+
+    @_op_greedy_generate.register_fake
+    def _(handle, enc_out, prompt, max_length, timestamps):
+        return enc_out.new_empty((enc_out.shape[0], max_length - len(prompt) + 1), dtype=torch.int32)
+
+
+_MODELS: dict = {}
+
+
+# --------------------------------------------------------------------------------------------
+class BatchFeature(dict):
+    """Minimal stand-in for transformers.BatchFeature (dict with attribute access and .to)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def to(self, *a, **kw):
+        return BatchFeature({k: (v.to(*a, **kw) if torch.is_tensor(v) else v) for k, v in self.items()})
+
+
+class B200WhisperFeatureExtractor:
+    """Drop-in for WhisperFeatureExtractor on the reference's call sites
+    (ref: training/run_pseudo_labelling.py:739-741; prefiltering/validator_inference.py:57-69).
+    The log-mel runs in the K1 CUDA kernel; `device` selects the GPU ("cuda", "cuda:1")."""
+
+    model_input_names = ["input_features"]
+
+    def __init__(self, feature_size: int = 80, sampling_rate: int = SAMPLING_RATE, hop_length: int = 160,
+                 chunk_length: int = 30, n_fft: int = 400, padding_value: float = 0.0, device: str = "cuda", **kwargs):
+        if (sampling_rate, hop_length, chunk_length, n_fft) != (16000, 160, 30, 400):
+            raise NotImplementedError("the B200 log-mel kernel is specialised for 16 kHz / n_fft 400 / hop 160 / 30 s")
+        if feature_size not in (80, 128):
+            raise ValueError("feature_size must be 80 or 128")
+        self.feature_size = feature_size
+        self.sampling_rate = sampling_rate
+        self.hop_length = hop_length
+        self.chunk_length = chunk_length
+        self.n_fft = n_fft
+        self.n_samples = N_SAMPLES
+        self.nb_max_frames = N_FRAMES
+        self.padding_value = padding_value
+        self.device = device
+
+    @classmethod
+    def from_hf(cls, hf_fe, device: str = "cuda"):
+        return cls(feature_size=hf_fe.feature_size, sampling_rate=hf_fe.sampling_rate, hop_length=hf_fe.hop_length,
+                   chunk_length=hf_fe.chunk_length, n_fft=hf_fe.n_fft, device=device)
+
+    def __call__(self, raw_speech, sampling_rate: Optional[int] = None, return_tensors: Optional[str] = None,
+                 device: Optional[str] = None, truncation: bool = True, padding: str = "max_length", **kwargs):
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            # same message shape as HF (feature_extraction_whisper.py:261-267)
+            raise ValueError(
+                f"The model corresponding to this feature extractor: {self.__class__.__name__} was trained using a "
+                f"sampling rate of {self.sampling_rate}. Please make sure that the provided `raw_speech` input was "
+                f"sampled with {self.sampling_rate} and not {sampling_rate}.")
+        if kwargs.get("do_normalize") or kwargs.get("return_attention_mask") or kwargs.get("return_token_timestamps"):
+            raise NotImplementedError("do_normalize / attention masks are not on the reference's call path")
+        dev = device if device not in (None, "cpu") else self.device
+        pcm, n_valid = self._to_device_batch(raw_speech, dev)
+        feats = log_mel(pcm, n_valid, self.feature_size)
+        if return_tensors == "pt":
+            out = feats
+        elif return_tensors in (None, "np"):
+            arr = feats.cpu().numpy()
+            out = arr if return_tensors == "np" else [a for a in arr]
+        else:
+            raise ValueError(f"unsupported return_tensors={return_tensors!r}")
+        return BatchFeature({"input_features": out})
+
+    def _to_device_batch(self, raw_speech, dev):
+        if torch.is_tensor(raw_speech):
+            t = raw_speech
+            if t.dim() == 1:
+                t = t[None]
+            if t.dim() != 2:
+                raise ValueError("Only mono-channel audio is supported for input to " + self.__class__.__name__)
+            if t.dtype == torch.float64:
+                t = t.float()
+            if t.dtype not in (torch.int16, torch.float32):
+                t = t.float()
+            return t.to(dev, non_blocking=True), None
+        if isinstance(raw_speech, np.ndarray) and raw_speech.ndim == 2:
+            rows = list(raw_speech)
+        elif isinstance(raw_speech, np.ndarray) and raw_speech.ndim > 2:
+            raise ValueError("Only mono-channel audio is supported for input to " + self.__class__.__name__)
+        elif isinstance(raw_speech, (list, tuple)) and len(raw_speech) and isinstance(raw_speech[0], (np.ndarray, list, tuple)):
+            rows = [np.asarray(r) for r in raw_speech]
+        else:
+            rows = [np.asarray(raw_speech)]
+        is_i16 = all(r.dtype == np.int16 for r in rows)
+        n_max = min(max(len(r) for r in rows), N_SAMPLES)
+        n_max = max(n_max, 8)
+        buf = np.zeros((len(rows), n_max), dtype=np.int16 if is_i16 else np.float32)
+        n_valid = np.zeros(len(rows), dtype=np.int32)
+        for i, r in enumerate(rows):
+            if r.ndim != 1:
+                raise ValueError("Only mono-channel audio is supported for input to " + self.__class__.__name__)
+            n = min(len(r), N_SAMPLES)          # truncation to 30 s
+            buf[i, :n] = r[:n]
+            n_valid[i] = n
+        return torch.from_numpy(buf).to(dev), torch.from_numpy(n_valid).to(dev)
+
+    def pad(self, processed_features, padding="longest", return_tensors: Optional[str] = None, **kwargs):
+        """ref: training/run_pseudo_labelling.py:370-374, prefiltering/validator_inference.py:65-69 —
+        every window is already 3000 frames long, so this only stacks."""
+        feats = processed_features["input_features"] if isinstance(processed_features, dict) else \
+            [f["input_features"] for f in processed_features]
+        if torch.is_tensor(feats):
+            stacked = feats
+        else:
+            stacked = torch.stack([torch.as_tensor(f) for f in feats])
+        if return_tensors in (None, "np"):
+            stacked = stacked.cpu().numpy()
+        return BatchFeature({"input_features": stacked})
+
+
+# --------------------------------------------------------------------------------------------
+_LANG_NAMES = {"chinese": "zh", "mandarin": "zh", "english": "en", "japanese": "ja", "cantonese": "yue", "korean": "ko",
+               "german": "de", "french": "fr", "spanish": "es"}
+
+
+class B200WhisperForConditionalGeneration:
+    """Drop-in for the `WhisperForConditionalGeneration` object the reference scripts hold, on the
+    surface they touch: .eval(), .to(), .config, .generation_config, .generate(...), .module."""
+
+    def __init__(self, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda"):
+        cfg = hf_model.config
+        self.config = cfg
+        self.generation_config = hf_model.generation_config
+        self.dtype = dtype
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("dtype must be torch.bfloat16 (tcgen05 path) or torch.float32 (check mode)")
+        self.device = torch.device(device if ":" in str(device) else f"cuda:{torch.cuda.current_device()}")
+        self.ctx = _lib.Context.get(_dev_index(self.device))
+        from .configs import WhisperShape
+        if cfg.encoder_attention_heads != cfg.decoder_attention_heads or cfg.encoder_ffn_dim != cfg.decoder_ffn_dim:
+            raise NotImplementedError("encoder/decoder widths must match (true for every Whisper checkpoint)")
+        self.shape = WhisperShape("hf", cfg.num_mel_bins, cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_attention_heads,
+                                  cfg.encoder_layers, cfg.decoder_layers, cfg.vocab_size, cfg.max_target_positions)
+        self.max_batch = max_batch
+        desc = _lib.ModelDesc(cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_attention_heads, cfg.encoder_layers,
+                              cfg.decoder_layers, cfg.num_mel_bins, cfg.vocab_size, cfg.max_target_positions,
+                              _TORCH2TW[dtype], max_batch)
+        # weights snapshot (after any embedding surgery such as utils/model_utils.py:4-14) -> device
+        sd = hf_model.state_dict()
+        keep, table = [], []
+        with torch.cuda.device(self.device):
+            for name, t in sd.items():
+                if not name.startswith("model."):
+                    continue                      # proj_out.weight is tied to embed_tokens
+                t = t.detach()
+                if t.dtype not in (torch.float32, torch.bfloat16):
+                    t = t.float()
+                t = t.to(self.device).contiguous()
+                keep.append(t)
+                table.append(_lib.Weight(name.encode(), t.data_ptr(), _TORCH2TW[t.dtype], t.numel()))
+            torch.cuda.synchronize(self.device)
+            arr = (_lib.Weight * len(table))(*table)
+            h = C.c_void_p()
+            self.ctx.check(self.ctx.lib.tw_model_load(self.ctx.handle, C.byref(desc), arr, len(table), C.byref(h)))
+        self.handle = h
+        del keep
+        self._id = id(self)
+        _MODELS[self._id] = self
+        self.training = False
+
+    @classmethod
+    def from_hf(cls, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda"):
+        return cls(hf_model, dtype=dtype, max_batch=max_batch, device=device)
+
+    # ---- nn.Module-ish surface the scripts touch
+    def eval(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    @property
+    def module(self):          # `model.module.generate` under DDP wrapping (ref run_pseudo_labelling.py:917)
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.tw_model_free(self.handle)
+            self.handle = None
+            _MODELS.pop(self._id, None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_bytes(self) -> int:
+        return int(self.ctx.lib.tw_model_bytes(self.handle))
+
+    # ---- generation config plumbing (generation_whisper.py:1455-1608, :1774-1812)
+    def _init_tokens(self, language, task, return_timestamps):
+        gc = self.generation_config
+        is_multi = getattr(gc, "is_multilingual", None)
+        if is_multi is None or not hasattr(gc, "lang_to_id") or not hasattr(gc, "task_to_id"):
+            raise ValueError("The generation config is outdated: it needs `is_multilingual`, `lang_to_id`, `task_to_id` "
+                             "and `no_timestamps_token_id` (as generation_config.json of the released checkpoints has).")
+        toks = [self.config.decoder_start_token_id]
+        if not is_multi:
+            if language is not None or task is not None:
+                raise ValueError("Cannot specify `task` or `language` for an English-only model.")
+        else:
+            lang = "en" if language is None else str(language).lower()
+            if lang in gc.lang_to_id:
+                lang_tok = lang
+            elif f"<|{lang}|>" in gc.lang_to_id:
+                lang_tok = f"<|{lang}|>"
+            elif lang in _LANG_NAMES and f"<|{_LANG_NAMES[lang]}|>" in gc.lang_to_id:
+                lang_tok = f"<|{_LANG_NAMES[lang]}|>"
+            else:
+                raise ValueError(f"Unsupported language: {language}. Language should be one of: "
+                                 f"{sorted(gc.lang_to_id.keys())[:8]}...")
+            toks.append(gc.lang_to_id[lang_tok])
+            t = "transcribe" if task is None else task
+            if t not in gc.task_to_id:
+                raise ValueError(f"The `{t}` task is not supported. The task should be one of `{list(gc.task_to_id)}`")
+            toks.append(gc.task_to_id[t])
+        if not return_timestamps:
+            toks.append(gc.no_timestamps_token_id)
+        return toks
+
+    def _rules(self, return_timestamps):
+        gc = self.generation_config
+        eos = gc.eos_token_id if not isinstance(gc.eos_token_id, (list, tuple)) else gc.eos_token_id[0]
+        pad = gc.pad_token_id if gc.pad_token_id is not None else eos
+        return dict(suppress=list(getattr(gc, "suppress_tokens", None) or []),
+                    begin_suppress=list(getattr(gc, "begin_suppress_tokens", None) or []),
+                    eos=int(eos), pad=int(pad),
+                    timestamp_begin=(gc.no_timestamps_token_id + 1) if return_timestamps else None,
+                    no_timestamps=int(gc.no_timestamps_token_id),
+                    max_initial_ts=getattr(gc, "max_initial_timestamp_index", None))
+
+    # ---- device-level entry points
+    def encode(self, mel: torch.Tensor, tap_layer: int = -1):
+        """mel [B, n_mel, 3000] float32 cuda -> enc_out [B,1500,d] (model dtype); with tap_layer >= 0 also
+        returns the fp32 residual stream after that many layers."""
+        if mel.shape[-1] != N_FRAMES or mel.shape[-2] != self.shape.n_mel:
+            # HF raises ValueError on a wrong feature length (modeling_whisper.py:613-617)
+            raise ValueError(f"Whisper expects the mel input features to be of length {N_FRAMES}, but found "
+                             f"{mel.shape[-1]}. Make sure to pad the input mel features to {N_FRAMES}.")
+        mel = mel.to(self.device, torch.float32).contiguous()
+        B = mel.shape[0]
+        out = torch.empty((B, 1500, self.shape.d_model), dtype=self.dtype, device=self.device)
+        tap = torch.empty((B, 1500, self.shape.d_model), dtype=torch.float32, device=self.device) if tap_layer >= 0 else None
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.ctx.lib.tw_encode(self.handle, mel.data_ptr(), B, out.data_ptr(), tap_layer,
+                                                  tap.data_ptr() if tap is not None else None, _stream_ptr(self.device)))
+        return (out, tap) if tap_layer >= 0 else out
+
+    def decode(self, enc_out: torch.Tensor, prompt, max_length: int, timestamps: bool, forced: Optional[torch.Tensor] = None,
+               tap_steps: int = 0):
+        B = enc_out.shape[0]
+        n_gen = max_length - len(prompt)
+        if n_gen <= 0 or max_length > self.shape.max_target:
+            raise ValueError(f"The length of the prompt ({len(prompt)}) plus the new tokens must fit max_length "
+                             f"<= max_target_positions ({self.shape.max_target}); got max_length={max_length}")
+        enc_out = enc_out.to(self.device, self.dtype).contiguous()
+        toks = torch.empty((B, n_gen), dtype=torch.int32, device=self.device)
+        lens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        tap = torch.empty((tap_steps, B, self.shape.vocab), dtype=torch.float32, device=self.device) if tap_steps else None
+        if forced is not None:
+            forced = forced.to(self.device, torch.int32).contiguous()
+            assert forced.shape == (B, n_gen)
+        r = self._rules(timestamps)
+        rules, keep = _lib.make_rules(r["suppress"], r["begin_suppress"], r["eos"], r["pad"], r["timestamp_begin"],
+                                      r["no_timestamps"], r["max_initial_ts"])
+        p = (C.c_int32 * len(prompt))(*prompt)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.ctx.lib.tw_decode_greedy(
+                self.handle, enc_out.data_ptr(), B, p, len(prompt), C.byref(rules), max_length, toks.data_ptr(),
+                lens.data_ptr(), forced.data_ptr() if forced is not None else None,
+                tap.data_ptr() if tap is not None else None, tap_steps, _stream_ptr(self.device)))
+        del keep
+        return (toks, lens, tap) if tap_steps else (toks, lens)
+
+    def transcribe_pcm(self, pcm_host: torch.Tensor, max_length: int, return_timestamps: bool = False, language="zh",
+                       task="transcribe", n_valid: Optional[torch.Tensor] = None, out_tokens: Optional[torch.Tensor] = None,
+                       out_lengths: Optional[torch.Tensor] = None):
+        """Whole path from HOST int16 PCM [B, 480000] (pinned for async copies) to HOST token ids:
+        one C-ABI call = fe(...) + generate(...) of the reference."""
+        if pcm_host.dtype != torch.int16 or pcm_host.dim() != 2 or pcm_host.shape[1] != N_SAMPLES or pcm_host.is_cuda:
+            raise ValueError("transcribe_pcm expects a host int16 tensor [B, 480000]")
+        pcm_host = pcm_host.contiguous()
+        B = pcm_host.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        prompt = self._init_tokens(language, task, return_timestamps)
+        n_gen = max_length - len(prompt)
+        if n_gen <= 0 or max_length > self.shape.max_target:
+            raise ValueError("max_length must exceed the prompt and fit max_target_positions")
+        if out_tokens is None:
+            out_tokens = torch.empty((B, n_gen), dtype=torch.int32).pin_memory()
+            out_lengths = torch.empty((B,), dtype=torch.int32).pin_memory()
+        r = self._rules(return_timestamps)
+        rules, keep = _lib.make_rules(r["suppress"], r["begin_suppress"], r["eos"], r["pad"], r["timestamp_begin"],
+                                      r["no_timestamps"], r["max_initial_ts"])
+        p = (C.c_int32 * len(prompt))(*prompt)
+        nv = n_valid.contiguous().data_ptr() if n_valid is not None else None
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.ctx.lib.tw_transcribe_host(
+                self.handle, pcm_host.data_ptr(), nv, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
+                out_lengths.data_ptr(), _stream_ptr(self.device)))
+        del keep
+        return out_tokens, out_lengths
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 5)()
+        self.ctx.lib.tw_last_stage_ms(self.handle, buf)
+        return dict(zip(("logmel", "encoder", "cross_kv", "decode", "total"), [float(x) for x in buf]))
+
+    # ---- the reference's call
+    @torch.no_grad()
+    def generate(self, input_features=None, *, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None,
+                 num_beams: int = 1, return_timestamps: Optional[bool] = None, language: Optional[str] = None,
+                 task: Optional[str] = None, attention_mask=None, return_prompt: bool = False, **kwargs):
+        """ref: training/run_pseudo_labelling.py:864-876,917-918; prefiltering/validator_inference.py:41-47,78.
+        Returns a LongTensor [B, L] of generated ids (after the forced prompt, as transformers >= 4.46 / 5.x
+        return them; `return_prompt=True` prepends the prompt, the 4.45 layout ref :629,1009-1010 expects),
+        EOS stripped, right-padded with pad_token_id to the batch maximum.  One 30 s window per row."""
+        if num_beams not in (None, 1):
+            raise NotImplementedError("twb200 implements greedy decoding only (num_beams=1), as the reference's "
+                                      "pseudo-labelling launchers use")
+        for k in ("do_sample", "prompt_ids", "assistant_model", "temperature", "logits_processor"):
+            if kwargs.get(k):
+                raise NotImplementedError(f"generate(..., {k}=...) is not on the reference's path")
+        if input_features is None:
+            raise ValueError("input_features is required")
+        feats = torch.as_tensor(input_features)
+        if feats.dim() != 3:
+            raise ValueError("input_features must be [batch, n_mel, 3000]")
+        if feats.shape[-1] != N_FRAMES:
+            raise ValueError(f"Whisper expects the mel input features to be of length {N_FRAMES}, but found "
+                             f"{feats.shape[-1]}. Make sure to pad the input mel features to {N_FRAMES}.")
+        ts = bool(return_timestamps) if return_timestamps is not None else False
+        prompt = self._init_tokens(language, task, ts)
+        if max_length is None:
+            if max_new_tokens is not None:
+                max_length = len(prompt) + max_new_tokens
+            else:
+                max_length = getattr(self.generation_config, "max_length", None) or self.shape.max_target
+        if max_length > self.shape.max_target:
+            raise ValueError(f"max_length={max_length} exceeds max_target_positions={self.shape.max_target}")
+        pad = self._rules(ts)["pad"]
+        rows, lens_all = [], []
+        for s in range(0, feats.shape[0], self.max_batch):
+            chunk = feats[s:s + self.max_batch]
+            enc = self.encode(chunk.to(self.device).float())
+            toks, lens = self.decode(enc, prompt, max_length, ts)
+            rows.append(toks)
+            lens_all.append(lens)
+        toks = torch.cat(rows).long()
+        lens = torch.cat(lens_all).long()
+        L = int(lens.max().item()) if lens.numel() else 0
+        toks = toks[:, :L]
+        ar = torch.arange(L, device=toks.device)[None, :]
+        toks = torch.where(ar < lens[:, None], toks, torch.full_like(toks, pad))
+        if return_prompt:
+            toks = torch.cat([torch.tensor(prompt, device=toks.device).expand(toks.shape[0], -1), toks], dim=1)
+        return toks if feats.is_cuda else toks.cpu()
+
+    # forward() (training) is out of scope
+
+
+_register_torch_ops()

@@ -1,0 +1,131 @@
+"""CPU (-m "not gpu"): the C-ABI library builds, loads and exports every symbol include/twb200.h
+declares; host-side logic (prompt tokens, rules, batch packing, error behaviour) without a GPU."""
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from taiwan_whisper_b200 import lib as twlib
+from taiwan_whisper_b200.build import build
+from taiwan_whisper_b200.configs import SHAPES, token_ids
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    build()
+    return twlib.load_library()
+
+
+def test_header_symbols_exported(library):
+    hdr = open(os.path.join(ROOT, "include", "twb200.h")).read()
+    declared = re.findall(r"^TW_API [\w\s\*]+?\b(tw_\w+)\(", hdr, flags=re.M)
+    assert len(declared) >= 14
+    assert sorted(declared) == sorted(twlib.EXPORTS)
+    for name in declared:
+        assert hasattr(library, name), name
+    assert library.tw_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu(library):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception) as e:
+        twlib.Context(0)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_sass_is_blackwell_native():
+    """the built library carries tcgen05 / TMA code (SASS mnemonics per B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", twlib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnem in sass, mnem
+
+
+def _fake_model(vocab=51866, multilingual=True):
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration as M
+    ids = token_ids(vocab)
+    m = M.__new__(M)
+    gc = types.SimpleNamespace(is_multilingual=multilingual, lang_to_id=dict(ids.lang_to_id),
+                               task_to_id={"transcribe": ids.transcribe, "translate": ids.translate},
+                               no_timestamps_token_id=ids.notimestamps, eos_token_id=ids.eos, pad_token_id=ids.pad,
+                               suppress_tokens=[1, 2, 7], begin_suppress_tokens=[220, ids.eos], max_initial_timestamp_index=50)
+    m.generation_config = gc
+    m.config = types.SimpleNamespace(decoder_start_token_id=ids.sot)
+    m.handle = None
+    return m, ids
+
+
+def test_init_tokens_match_reference_prompt():
+    m, ids = _fake_model(51866)
+    assert m._init_tokens("zh", "transcribe", False) == [50258, 50260, 50360, 50364]
+    assert m._init_tokens("<|zh|>", "transcribe", True) == [50258, 50260, 50360]
+    assert m._init_tokens("chinese", None, True) == [50258, 50260, 50360]
+    m2, ids2 = _fake_model(51865)
+    assert m2._init_tokens("zh", "transcribe", False) == [50258, 50260, 50359, 50363]
+    with pytest.raises(ValueError):
+        m._init_tokens("klingon", "transcribe", False)
+    with pytest.raises(ValueError):
+        m._init_tokens("zh", "summarise", False)
+    m3, _ = _fake_model(51865, multilingual=False)
+    with pytest.raises(ValueError):
+        m3._init_tokens("zh", "transcribe", False)
+
+
+def test_rules_struct():
+    m, ids = _fake_model(51866)
+    r = m._rules(True)
+    assert r["timestamp_begin"] == ids.timestamp_begin == 50365 and r["eos"] == 50257 and r["max_initial_ts"] == 50
+    assert m._rules(False)["timestamp_begin"] is None
+    s, keep = twlib.make_rules(r["suppress"], r["begin_suppress"], r["eos"], r["pad"], r["timestamp_begin"],
+                               r["no_timestamps"], r["max_initial_ts"])
+    assert s.n_suppress == 3 and s.n_begin_suppress == 2 and s.timestamp_begin == 50365
+    assert [s.suppress[i] for i in range(3)] == [1, 2, 7]
+
+
+def test_token_ids_tables():
+    a, b = token_ids(51865), token_ids(51866)
+    assert a.lang_to_id["<|zh|>"] == b.lang_to_id["<|zh|>"] == 50260      # ref: utils/test_hg_whisper.py:55-56
+    assert len(a.lang_to_id) == 99 and len(b.lang_to_id) == 100 and b.lang_to_id["<|yue|>"] == 50358
+    assert a.timestamp_begin == 50364 and b.timestamp_begin == 50365
+    assert a.timestamp_begin + 1500 == 51864 and b.timestamp_begin + 1500 == 51865
+    with pytest.raises(ValueError):
+        token_ids(1000)
+
+
+def test_feature_extractor_host_logic():
+    from taiwan_whisper_b200.host import B200WhisperFeatureExtractor
+    fe = B200WhisperFeatureExtractor(feature_size=128)
+    assert fe.sampling_rate == 16000 and fe.model_input_names == ["input_features"] and fe.n_samples == 480000
+    with pytest.raises(ValueError):
+        fe(np.zeros(16000, np.float32), sampling_rate=8000)
+    with pytest.raises(ValueError):
+        B200WhisperFeatureExtractor(feature_size=64)
+    with pytest.raises(NotImplementedError):
+        B200WhisperFeatureExtractor(feature_size=80, hop_length=128)
+    # batch packing (no kernel call): ragged rows, truncation at 30 s
+    rows = [np.ones(10, np.float32), np.ones(500000, np.float32)]
+    buf, nv = fe._to_device_batch(rows, "cpu")
+    assert buf.shape == (2, 480000) and nv.tolist() == [10, 480000] and buf[0, 10:].abs().sum() == 0
+    padded = fe.pad({"input_features": [np.zeros((128, 3000), np.float32)] * 3}, return_tensors="pt")
+    assert padded["input_features"].shape == (3, 128, 3000)
+
+
+def test_shapes_sheet():
+    lv3 = SHAPES["large-v3"]
+    assert (lv3.d_model, lv3.ffn, lv3.heads, lv3.enc_layers, lv3.dec_layers, lv3.n_mel, lv3.vocab) == \
+        (1280, 5120, 20, 32, 32, 128, 51866)
+    assert SHAPES["distil-large-v3"].dec_layers == 2     # ref: training/create_student_model.py:147-148
+    for s in SHAPES.values():
+        assert s.head_dim == 64

@@ -1,0 +1,281 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.
+
+Tolerances (north_star): log-mel 1e-4 abs; encoder hidden states 1e-4 in fp32 check mode and 2e-2
+relative in bf16; greedy ids bit-identical in fp32 check mode; bf16 token agreement measured
+teacher-forced (see DESIGN.md §parity for why free-running agreement is not defined for
+random-init weights: the reference's own bf16 run agrees with its fp32 run on ~74 % of tokens).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_np
+from taiwan_whisper_b200.configs import SHAPES, token_ids
+from taiwan_whisper_b200.synth import dequantise, edge_case_clips, synth_batch
+from tests.helpers import prompt_ids
+
+pytestmark = pytest.mark.gpu
+
+LOGMEL_TOL = 1e-4
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the -m gpu tests must run on a B200 (there is no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------ log-mel
+@pytest.mark.parametrize("n_mel", [80, 128])
+@pytest.mark.parametrize("in_dtype", ["i16", "f32"])
+def test_logmel_vs_oracle(n_mel, in_dtype):
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    clips = list(synth_batch(0, 3)) + list(edge_case_clips().values())
+    pcm = np.stack(clips)
+    ref = logmel_np.log_mel(dequantise(pcm), n_mel)
+    x = torch.from_numpy(pcm if in_dtype == "i16" else dequantise(pcm)).cuda()
+    out = log_mel(x, None, n_mel).cpu().numpy()
+    assert out.shape == ref.shape and out.dtype == np.float32
+    err = np.abs(out - ref).reshape(len(clips), -1).max(1)
+    assert err.max() < LOGMEL_TOL, err
+    assert np.all(out[3] == np.float32(-1.5))          # silence
+
+
+def test_logmel_vs_golden(golden_dir):
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    clips = {f"synth{i}": c for i, c in enumerate(synth_batch(0, 2))}
+    clips.update(edge_case_clips())
+    for n_mel in (80, 128):
+        g = np.load(os.path.join(golden_dir, f"logmel_{n_mel}.npz"))
+        x = torch.from_numpy(np.stack(list(clips.values()))).cuda()
+        out = log_mel(x, None, n_mel).cpu().numpy()
+        for i, name in enumerate(clips):
+            assert np.abs(out[i][:, ::16] - g[name + "_sub"]).max() < LOGMEL_TOL, (n_mel, name)
+
+
+def test_logmel_ragged_and_long():
+    """short rows are zero-extended, long rows truncated to 30 s, n_valid masks the tail."""
+    _cuda()
+    from taiwan_whisper_b200.host import B200WhisperFeatureExtractor
+    fe = B200WhisperFeatureExtractor(feature_size=80)
+    a = dequantise(synth_batch(11, 1)[0])
+    rows = [a[:80_000], a, np.concatenate([a, a[:1000]]), a[:12_345], np.zeros(0, np.float32)]
+    out = fe(rows, sampling_rate=16000, return_tensors="np")["input_features"]
+    ref = np.stack([logmel_np.log_mel(logmel_np.pad_or_trim(r), 80) for r in rows])
+    assert out.shape == (5, 80, 3000)
+    assert np.abs(out - ref).max() < LOGMEL_TOL
+    with pytest.raises(ValueError):
+        fe(rows[0], sampling_rate=8000)
+
+
+def test_logmel_empty_batch():
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    out = log_mel(torch.zeros((0, 480000), dtype=torch.int16, device="cuda"), None, 128)
+    assert out.shape == (0, 128, 3000)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 128), (1500, 1280, 1280), (300, 384, 240), (64, 1280, 1280), (257, 520, 1536),
+                                   (3000, 5120, 1280), (4, 51866, 384)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_gemm_tcgen05_vs_torch(M, N, K, mode):
+    _cuda()
+    from tests.gpu_common import gemm_debug
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + mode)
+    A = (torch.randn((M, K), device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g) * 0.1
+    C0 = torch.randn((M, N), device="cuda", generator=g)
+    period = 100
+    pos = torch.randn((period, N), device="cuda", generator=g)
+    acc = A.float() @ W.float().T + bias
+    if mode == 0:
+        ref = acc
+    elif mode == 1:
+        ref = torch.nn.functional.gelu(acc)
+    elif mode == 2:
+        ref = C0 + acc
+    elif mode == 3:
+        ref = torch.nn.functional.gelu(acc) + pos[torch.arange(M, device="cuda") % period]
+    else:
+        ref = acc
+    out = gemm_debug(A, W, bias, mode, True, C_init=C0, pos=pos, period=period).float()
+    tol = 2e-2 if mode in (0, 1) else 2e-3          # bf16 output rounding vs fp32 output
+    err = (out - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+    simt = gemm_debug(A, W, bias, mode, False, C_init=C0, pos=pos, period=period).float()
+    assert (simt - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_fp32_check_mode_vs_torch():
+    _cuda()
+    from tests.gpu_common import gemm_debug
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (M, N, K) in [(130, 70, 33), (1500, 384, 384), (3, 51865, 128)]:
+        A = torch.randn((M, K), device="cuda", generator=g)
+        W = torch.randn((N, K), device="cuda", generator=g) * 0.05
+        bias = torch.randn((N,), device="cuda", generator=g)
+        ref = (A.double() @ W.double().T + bias.double()).float()
+        out = gemm_debug(A, W, bias, 4, False)
+        assert (out - ref).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ encoder
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+def test_encoder_fp32_check_mode(shape_name):
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    sh = SHAPES[shape_name]
+    pcm, mel, ora = oracle_run(shape_name, 2, 24)
+    m = b200_model(shape_name, "f32")
+    melt = torch.from_numpy(mel).cuda()
+    for layer in range(sh.enc_layers + 1):
+        enc, tap = m.encode(melt, tap_layer=layer)
+        for b in range(2):
+            ref = ora[b]["taps"][layer]
+            err = np.abs(tap[b].cpu().numpy() - ref).max() / np.abs(ref).max()
+            assert err < 1e-4, (layer, b, err)
+    enc = m.encode(melt).cpu().numpy()
+    for b in range(2):
+        assert np.abs(enc[b] - ora[b]["enc"]).max() < 1e-4 * max(1.0, np.abs(ora[b]["enc"]).max())
+
+
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+def test_encoder_bf16(shape_name):
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    pcm, mel, ora = oracle_run(shape_name, 2, 24)
+    m = b200_model(shape_name, "bf16")
+    enc = m.encode(torch.from_numpy(mel).cuda()).float().cpu().numpy()
+    for b in range(2):
+        ref = ora[b]["enc"]
+        rel = np.linalg.norm(enc[b] - ref) / np.linalg.norm(ref)
+        assert rel < 2e-2, rel
+
+
+def test_encoder_rejects_wrong_length():
+    _cuda()
+    from tests.gpu_common import b200_model
+    m = b200_model("micro128", "f32")
+    with pytest.raises(ValueError):
+        m.generate(torch.zeros((1, 128, 2999)), max_length=16, language="zh", task="transcribe")
+
+
+# ------------------------------------------------------------------------------------------ decode
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+@pytest.mark.parametrize("timestamps", [False, True])
+def test_greedy_tokens_fp32_bit_identical(shape_name, timestamps):
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    sh = SHAPES[shape_name]
+    max_length = 40
+    pcm, mel, ora = oracle_run(shape_name, 3, max_length, timestamps)
+    m = b200_model(shape_name, "f32")
+    ids = m.generate(torch.from_numpy(mel), max_length=max_length, num_beams=1, return_timestamps=timestamps,
+                     language="zh", task="transcribe").numpy()
+    for b in range(3):
+        ref = ora[b]["tokens"]
+        assert ids[b, :len(ref)].tolist() == ref, (b, ids[b].tolist(), ref)
+        assert np.all(ids[b, len(ref):] == token_ids(sh.vocab).pad)
+    # post-rules logits of the first steps (mask pattern identical, values within fp32 noise)
+    enc = m.encode(torch.from_numpy(mel).cuda())
+    toks, lens, tap = m.decode(enc, prompt_ids(sh.vocab, timestamps), max_length, timestamps, tap_steps=4)
+    tap = tap.cpu().numpy()
+    for s in range(4):
+        for b in range(3):
+            ref = ora[b]["logits"][s]
+            assert np.array_equal(np.isneginf(tap[s, b]), np.isneginf(ref)), (s, b)
+            fin = np.isfinite(ref)
+            assert np.abs(tap[s, b][fin] - ref[fin]).max() < 1e-4
+
+
+def test_tokens_vs_hf_golden(golden_dir):
+    _cuda()
+    from tests.gpu_common import b200_model
+    from taiwan_whisper_b200.host import B200WhisperFeatureExtractor
+    for shape_name in ("tiny", "micro128"):
+        g = np.load(os.path.join(golden_dir, f"model_{shape_name}.npz"))
+        sh = SHAPES[shape_name]
+        fe = B200WhisperFeatureExtractor(feature_size=sh.n_mel)
+        feats = fe(list(dequantise(synth_batch(0, 2))), sampling_rate=16000, return_tensors="pt")["input_features"]
+        m = b200_model(shape_name, "f32")
+        ids = m.generate(feats, max_length=int(g["max_length"]), num_beams=1, return_timestamps=False, language="zh",
+                         task="transcribe").cpu().numpy()
+        ref = g["tokens_nots"]
+        assert ids.shape == ref.shape and np.array_equal(ids, ref)
+
+
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+def test_tokens_bf16_teacher_forced(shape_name):
+    """bf16: feed the oracle's fp32 tokens back (teacher forcing) and compare the per-step argmax.
+    Positions whose fp32 top-1/top-2 margin is below the bf16 noise floor are excluded from the 99.5 % bar
+    (and counted separately)."""
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    sh = SHAPES[shape_name]
+    max_length = 64
+    pcm, mel, ora = oracle_run(shape_name, 3, max_length, False)
+    m = b200_model(shape_name, "bf16")
+    P = prompt_ids(sh.vocab, False)
+    n_gen = max_length - len(P)
+    forced = torch.tensor([o["tokens"][:n_gen] for o in ora], dtype=torch.int32)
+    enc = m.encode(torch.from_numpy(mel).cuda())
+    toks, lens = m.decode(enc, P, max_length, False, forced=forced)
+    toks = toks.cpu().numpy()
+    agree = solid = solid_agree = 0
+    for b in range(3):
+        for s in range(n_gen):
+            lg = ora[b]["logits"][s]
+            top2 = np.partition(lg[np.isfinite(lg)], -2)[-2:]
+            margin = top2[1] - top2[0]
+            ok = toks[b, s] == ora[b]["tokens"][s]
+            agree += ok
+            if margin > 0.02:
+                solid += 1
+                solid_agree += ok
+    total = 3 * n_gen
+    print(f"bf16 teacher-forced agreement {agree}/{total}; margin>0.02: {solid_agree}/{solid}")
+    assert solid > 0 and solid_agree / solid >= 0.995
+    assert agree / total >= 0.80
+
+
+def test_transcribe_host_path_matches_generate():
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    shape_name = "micro128"
+    sh = SHAPES[shape_name]
+    max_length = 32
+    pcm, mel, ora = oracle_run(shape_name, 3, 40, False)
+    m = b200_model(shape_name, "f32")
+    toks, lens = m.transcribe_pcm(torch.from_numpy(pcm).pin_memory(), max_length)
+    for b in range(3):
+        n = max_length - 4
+        assert toks[b, :n].tolist() == ora[b]["tokens"][:n]
+    ms = m.last_stage_ms()
+    assert ms["total"] > 0 and ms["encoder"] > 0
+
+
+def test_generate_argument_errors():
+    _cuda()
+    from tests.gpu_common import b200_model
+    m = b200_model("micro128", "f32")
+    f = torch.zeros((1, 128, 3000))
+    with pytest.raises(NotImplementedError):
+        m.generate(f, max_length=16, num_beams=4, language="zh", task="transcribe")
+    with pytest.raises(ValueError):
+        m.generate(f, max_length=16, language="xx-unknown", task="transcribe")
+    with pytest.raises(ValueError):
+        m.generate(f, max_length=1000, language="zh", task="transcribe")
+
+
+def test_torch_ops_registered():
+    _cuda()
+    import taiwan_whisper_b200.host  # noqa: F401
+    x = torch.from_numpy(synth_batch(0, 1)).cuda()
+    out = torch.ops.twb200.log_mel(x, 80)
+    assert out.shape == (1, 80, 3000)
