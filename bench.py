@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — RTFx (audio-seconds per second) of whisper-large-v3 pseudo-labelling on N B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference's own CPU path (HF)
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # one rank per GPU
+
+A "step" = one batch (BASELINE.json configs[1]: whisper-large-v3, bf16, 64 synthetic 30 s clips per GPU,
+greedy zh/transcribe, max_length 256 => 252 generated tokens per clip; random-init weights never emit EOS)
+through the whole hot path: log-mel -> encoder -> cross-K/V -> KV-cached greedy decode.
+  value   inputs (int16 PCM) already resident in HBM, tokens left in HBM, CUDA-event timed
+  e2e     the same through the public host API `transcribe_pcm` (one C-ABI call, tw_transcribe_host):
+          pinned HOST PCM in, HOST token ids out, copies inside the timed region
+Multi-GPU: the utterance manifest is sharded (rank r owns clips [r*n, (r+1)*n)); no collective on the
+data path; one final all_gather of the token rows (inside the timed region); weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL = "large-v3"
+BATCH = 64
+MAX_LENGTH = 256           # ref: training/run-pseudo-labelling.sh:33
+CLIP_SECONDS = 30.0
+POOL_CLIPS = 64            # distinct synthetic clips per rank (a manifest maps ids onto the pool)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--max-length", type=int, default=MAX_LENGTH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (HF feature extractor + generate, fp32, all host
+    threads) on a bounded sample of the workload: each step = 1 clip of the batch, full token budget."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from oracle import hf_ref
+    from taiwan_whisper_b200.configs import SHAPES
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sh = SHAPES[args.model]
+    model = hf_ref.build_hf_model(sh, seed=1234)
+    fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
+    clips_per_step = 1
+    pcm = dequantise(synth_batch(0, clips_per_step * (args.steps + args.warmup)))
+
+    def step(i):
+        x = pcm[i * clips_per_step:(i + 1) * clips_per_step]
+        feats = hf_ref.hf_features(fe, x)
+        ids = hf_ref.hf_generate(model, feats, args.max_length, return_timestamps=False)
+        return ids.shape[1]
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    v = clips_per_step * args.steps * CLIP_SECONDS / dt
+    sample = f"{clips_per_step} clip per step of the {args.batch}-clip batch, full max_length={args.max_length}, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": "rtfx_audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whisper-{args.model} pseudo-labelling, {args.batch} x 30 s clips per GPU, greedy zh/transcribe, "
+                               f"max_length {args.max_length}", "sample": sample,
+                   "reference": "transformers WhisperFeatureExtractor + WhisperForConditionalGeneration.generate on host CPU"},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(args, hf_cpu):
+    """Reference (HF) on the box's host cores, 1 clip, full token budget (~20-40 s of CPU work)."""
+    import torch
+    from oracle import hf_ref
+    from taiwan_whisper_b200.configs import SHAPES
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sh = SHAPES[args.model]
+    fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
+    x = dequantise(synth_batch(0, 1))
+    t0 = time.perf_counter()
+    feats = hf_ref.hf_features(fe, x)
+    hf_ref.hf_generate(hf_cpu, feats, args.max_length, return_timestamps=False)
+    dt = time.perf_counter() - t0
+    return {"value": CLIP_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+            "sample": f"1 of the {args.batch} clips, full max_length={args.max_length}, HF transformers fp32 generate + feature "
+                      f"extractor, {dt:.1f} s"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import hf_ref            # only for building the HF model object + the cpu_baseline leg
+    from taiwan_whisper_b200.configs import SHAPES
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration, log_mel
+    from taiwan_whisper_b200.synth import synth_batch
+
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sh = SHAPES[args.model]
+    B, K, W = args.batch, args.steps, args.warmup
+
+    # random-init weights of the architecture (HF init), built directly on the GPU
+    with torch.device(dev):
+        hf = hf_ref.build_hf_model(sh, seed=1234)
+    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev))
+    hf_cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        hf_cpu = hf.to("cpu")
+    del hf
+    torch.cuda.empty_cache()
+
+    # manifest shard of this rank: clip ids [rank*n, (rank+1)*n) mapped onto a pool of distinct synthetic clips
+    pool = torch.from_numpy(synth_batch(rank * POOL_CLIPS, POOL_CLIPS)).pin_memory()
+    n_steps_total = W + K
+
+    def batch_host(i):
+        idx = [(i * B + j) % POOL_CLIPS for j in range(B)]
+        return pool[idx].pin_memory() if idx != list(range(B)) else pool[:B]
+
+    host_batches = [batch_host(i) for i in range(n_steps_total)]
+    dev_batches = [hb.to(dev) for hb in host_batches[:2]]           # resident inputs (alternate)
+    prompt = model._init_tokens("zh", "transcribe", False)
+    n_gen = args.max_length - len(prompt)
+
+    def step_device(i):
+        pcm = dev_batches[i % len(dev_batches)]
+        mel = log_mel(pcm, None, sh.n_mel)
+        enc = model.encode(mel)
+        return model.decode(enc, prompt, args.max_length, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (`value`)
+    for i in range(W):
+        step_device(i)
+    model.profile(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = model.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    outs = []
+    for i in range(K):
+        outs.append(step_device(W + i))
+    if world > 1:       # final result gather (the only collective of the path)
+        toks = torch.cat([o[0] for o in outs])
+        gathered = [torch.empty_like(toks) for _ in range(world)]
+        dist.all_gather(gathered, toks)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    prof_ms, prof_n = model.profile(False)
+    stage = model.last_stage_ms()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * B * CLIP_SECONDS / (ms_max / 1000.0)
+
+    # ---------------- end-to-end timing through the host API (`e2e`)
+    e2e = None
+    if not args.no_e2e:
+        out_tok = torch.empty((B, n_gen), dtype=torch.int32).pin_memory()
+        out_len = torch.empty((B,), dtype=torch.int32).pin_memory()
+        for i in range(min(W, 1)):
+            model.transcribe_pcm(host_batches[i], args.max_length, out_tokens=out_tok, out_lengths=out_len)
+        barrier()
+        e0.record()
+        for i in range(K):
+            model.transcribe_pcm(host_batches[W + i], args.max_length, out_tokens=out_tok, out_lengths=out_len)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        stage = model.last_stage_ms()
+        e2e = {"value": world * K * B * CLIP_SECONDS / (e2e_ms / 1000.0), "unit": "audio-s/s",
+               "h2d_bytes_per_step": int(host_batches[0].numel() * 2), "d2h_bytes_per_step": int(out_tok.numel() * 4 + out_len.numel() * 4),
+               "ms_per_step": e2e_ms / K, "api": "B200WhisperForConditionalGeneration.transcribe_pcm -> tw_transcribe_host"}
+
+    if rank == 0:
+        hbm, tf, which = peaks()
+        bytes_per_launch = B * 1500 * 2 * sh.d_model * 2          # K|V rows of one decoder layer for the batch, bf16
+        roof = None
+        if prof_n > 0:
+            ach = bytes_per_launch / (prof_ms / prof_n / 1000.0) / 1e9
+            roof = {"kernel": "decode_attention_partial (cross-attention K/V streaming, 1 launch per layer per token)",
+                    "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": which,
+                    "traffic": None, "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
+                    "algorithmic_bytes_per_launch": bytes_per_launch}
+        line = {
+            "metric": "rtfx_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"whisper-{args.model} pseudo-labelling: {B} x 30 s 16 kHz clips per GPU per step, log-mel + "
+                                   f"encoder + cross-K/V + greedy decode, zh/transcribe, max_length {args.max_length} "
+                                   f"({n_gen} generated tokens/clip)",
+                       "batch_per_gpu": B, "max_length": args.max_length, "weights": "random-init (HF init, seed 1234)",
+                       "parallelism": f"manifest sharded over {world} GPU(s), no data-path collective",
+                       "l2": "inputs larger than L2: each step streams >= 15 GB of K/V and weights (L2 is 126 MB)",
+                       "stage_ms_last_step": stage},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+        }
+        if hf_cpu is not None:
+            line["cpu_baseline"] = cpu_baseline(args, hf_cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,6 +148,11 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
  * (CUDA events on the call's stream): [0] log-mel, [1] encoder, [2] cross-K/V, [3] decode, [4] total. */
 TW_API int tw_last_stage_ms(tw_model* m, float out_ms[5]);
 
+/* In-situ CUDA-event timing of the path's dominant kernel (the decode cross-attention K/V streaming
+ * kernel, one sampled launch per decode step at the middle decoder layer).  Reads and resets the
+ * accumulated samples (either pointer may be NULL), then enables/disables sampling for later calls. */
+TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch);
+
 /* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
  * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,
  * 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU

@@ -290,15 +290,18 @@ decode_attention_combine(const float* __restrict__ partial, int nchunks, int H, 
 
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial, T* out,
-                      cudaStream_t st) {
+                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     const int nchunks = decode_attention_chunks(Tk);
     const size_t smem = (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float);   // <= 42 KB
     dim3 grid(nchunks, B);
+    if (ev0) cudaEventRecord(ev0, st);
     decode_attention_partial<T><<<grid, DA_WARPS * 32, smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, H, partial);
+    if (ev1) cudaEventRecord(ev1, st);
     decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, nchunks, H, out);
 }
-template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, int, int, float*, float*, cudaStream_t);
+template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, int, int, float*, float*, cudaStream_t,
+                                      cudaEvent_t, cudaEvent_t);
 template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, int, int, float*,
-                                              __nv_bfloat16*, cudaStream_t);
+                                              __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
 
 }  // namespace tw

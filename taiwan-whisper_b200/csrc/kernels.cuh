@@ -64,7 +64,7 @@ void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStrea
 // q T [B, q_stride]; partial workspace f32 [B * nchunks * H * 66]; out T [B, d].
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial,
-                      T* out, cudaStream_t st);
+                      T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 int decode_attention_chunks(int Tk);
 
 // ---- token selection (select.cu)

@@ -104,6 +104,10 @@ struct tw_model {
     int32_t* d_ids_tmp = nullptr;
     int32_t *d_out_tok = nullptr, *d_out_len = nullptr;
     int32_t* h_flag = nullptr;   // pinned
+    // in-situ timing of the dominant kernel (cross-attention K/V streaming) for bench.py's roofline
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    int prof_used = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
     bool ev_valid[6] = {false, false, false, false, false, false};
@@ -437,8 +441,14 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
             TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
             layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
             TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (m->prof_on && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
+                e0 = m->prof_ev[m->prof_used];
+                e1 = m->prof_ev[m->prof_used + 1];
+                m->prof_used += 2;
+            }
             decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, B, H, m->dpartial, att,
-                                st);
+                                st, e0, e1);
             TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
             layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
             TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
@@ -579,6 +589,7 @@ void tw_model_free(tw_model* m) {
     if (m->h_flag) cudaFreeHost(m->h_flag);
     for (auto& ev : m->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : m->prof_ev) cudaEventDestroy(ev);
     delete m;
 }
 
@@ -698,6 +709,37 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
         return TW_E_INVALID;
     }
     TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch) {
+    if (!m) return TW_E_INVALID;
+    if (total_ms || launches) {
+        float tot = 0.0f;
+        int n = 0;
+        for (int i = 0; i + 1 < m->prof_used; i += 2) {
+            float ms = 0.0f;
+            if (cudaEventSynchronize(m->prof_ev[i + 1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, m->prof_ev[i], m->prof_ev[i + 1]) == cudaSuccess) {
+                tot += ms;
+                ++n;
+            }
+        }
+        if (total_ms) *total_ms = tot;
+        if (launches) *launches = n;
+    }
+    if (bytes_per_launch) *bytes_per_launch = 0.0;   // caller computes B * 1500 * 2d * esz
+    m->prof_used = 0;
+    m->prof_on = enable != 0;
+    if (m->prof_on && m->prof_ev.empty()) {
+        m->prof_ev.resize(2 * 2048);
+        for (auto& ev : m->prof_ev) {
+            if (cudaEventCreate(&ev) != cudaSuccess) {
+                m->ctx->set_error(TW_E_CUDA, "tw_profile: cudaEventCreate failed");
+                return TW_E_CUDA;
+            }
+        }
+    }
     return TW_OK;
 }
 

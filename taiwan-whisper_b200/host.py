@@ -408,6 +408,13 @@ class B200WhisperForConditionalGeneration:
         del keep
         return out_tokens, out_lengths
 
+    def profile(self, enable: bool):
+        """Reads + resets the in-situ samples of the dominant kernel, then (de)activates sampling.
+        Returns (total_ms, launches)."""
+        ms, n = C.c_float(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.tw_profile(self.handle, 1 if enable else 0, C.byref(ms), C.byref(n), None))
+        return float(ms.value), int(n.value)
+
     def last_stage_ms(self):
         buf = (C.c_float * 5)()
         self.ctx.lib.tw_last_stage_ms(self.handle, buf)
