@@ -160,6 +160,15 @@ TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, d
 TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
                   int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);
 
+/* Test / profiling entry points for the two attention kernels of the path (device buffers):
+ *   decode attention: q [B, q_stride] (first H*64 elements used), K|V rows kv [B][Tk][2*H*64] with clip
+ *   stride kv_clip_stride elements -> out [B, H*64]   (softmax(q.K^T).V per head, q pre-scaled)
+ *   encoder attention: qkv [B*S, 3*H*64] -> out [B*S, H*64]; impl 0 = CUDA-core kernel, 1 = tcgen05 flash kernel (bf16) */
+TW_API int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride,
+                                     int Tk, int B, int H, int dtype, void* out, void* stream);
+TW_API int tw_debug_encoder_attention(tw_ctx* ctx, const void* qkv, void* out, int B, int S, int H, int dtype, int impl,
+                                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,137 +150,247 @@ template void encoder_attention_simt<float>(const float*, float*, int, int, int,
 template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
-// decode attention
-constexpr int DA_ROWS = 64;        // rows per CTA
-constexpr int DA_WARPS = 8;
+// decode attention — persistent TMA-bulk streaming kernel.
+//
+// The B*Tk rows of the K|V store are one flat stream split evenly over G = #SM CTAs (each CTA owns
+// R consecutive rows, possibly spanning a clip boundary).  A producer warp issues cp.async.bulk copies
+// of 8-row stages (8 x 2d elements, contiguous in HBM) into a shared-memory ring (mbarrier
+// complete_tx), 8 consumer warps take one row each per stage: per-head dot products with the query
+// held in registers, online softmax, P.V accumulation, all in fp32.  At the end of a clip segment the
+// warps merge through shared memory and emit one partial record (m, l, o[64]) per head; a small
+// second kernel merges the records of a clip.  Record index = cta + clip (unique, <= G + B - 2).
+constexpr int DA_WARPS = 8;        // consumer warps == rows per stage
 constexpr int DA_MAXSLOT = 5;      // ceil(H*8/32) with H <= 20
 constexpr int DA_PSTRIDE = HD + 2; // partial record: m, l, o[64]
+constexpr int DA_THREADS = (DA_WARPS + 1) * 32;
+constexpr int DA_MAX_STAGES = 8;
 
-int decode_attention_chunks(int Tk) { return ceil_div(Tk, DA_ROWS); }
+__device__ __forceinline__ uint32_t da_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void da_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void da_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void da_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void da_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DA_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DA_WAIT_DONE;\n"
+        "bra DA_WAIT_LOOP;\n"
+        "DA_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void da_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {
-    static __device__ __forceinline__ void load(const float* p, float* f) {
+    static __device__ __forceinline__ void load_shared(const float* p, float* f) {
         const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     }
 };
 template <> struct Vec8<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* f) {
-        uint4 raw;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(p));
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 t = __bfloat1622float2(h[i]);
-            f[2 * i] = t.x;
-            f[2 * i + 1] = t.y;
-        }
+    static __device__ __forceinline__ void load_shared(const __nv_bfloat16* p, float* f) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        // bf16 -> f32 is a 16-bit shift: low half and high half of each word
+        f[0] = __uint_as_float(raw.x << 16); f[1] = __uint_as_float(raw.x & 0xffff0000u);
+        f[2] = __uint_as_float(raw.y << 16); f[3] = __uint_as_float(raw.y & 0xffff0000u);
+        f[4] = __uint_as_float(raw.z << 16); f[5] = __uint_as_float(raw.z & 0xffff0000u);
+        f[6] = __uint_as_float(raw.w << 16); f[7] = __uint_as_float(raw.w & 0xffff0000u);
     }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(DA_WARPS * 32)
-decode_attention_partial(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk, int H,
-                         float* __restrict__ partial) {
-    extern __shared__ __align__(16) float da_smem[];          // [DA_WARPS][H][DA_PSTRIDE]
-    const int chunk = blockIdx.x, b = blockIdx.y, nchunks = gridDim.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = H * HD;
-    const int nslots = H * 8;
-    const T* kvb = kv + (int64_t)b * kv_clip_stride;
-    const T* qb = q + (int64_t)b * q_stride;
+struct DaPlan {
+    int G;        // CTAs
+    int R;        // rows per CTA
+    int stages;
+    size_t smem;
+};
+static DaPlan da_plan(int total_rows, int H, int esz, int sm_count) {
+    DaPlan p;
+    int g = ceil_div(total_rows, DA_WARPS);
+    if (g > sm_count) g = sm_count;
+    if (g < 1) g = 1;
+    p.G = g;
+    p.R = ceil_div(total_rows, g);
+    const size_t stage_bytes = (size_t)DA_WARPS * 2 * H * HD * esz;
+    const size_t merge_bytes = (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float);
+    int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
+    if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
+    if (st < 2) st = 2;
+    p.stages = st;
+    p.smem = st * stage_bytes + merge_bytes + 256;
+    return p;
+}
 
-    float qf[DA_MAXSLOT][8], of[DA_MAXSLOT][8], mrun[DA_MAXSLOT], lrun[DA_MAXSLOT];
-#pragma unroll
-    for (int s = 0; s < DA_MAXSLOT; ++s) {
-        const int slot = lane + 32 * s;
-        mrun[s] = -INFINITY;
-        lrun[s] = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { of[s][e] = 0.0f; qf[s][e] = 0.0f; }
-        if (slot < nslots) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) qf[s][e] = to_f32(qb[slot * 8 + e]);
+template <typename T>
+__global__ void __launch_bounds__(DA_THREADS, 1)
+decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk, int B,
+                        int H, int R, int stages, float* __restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char da_raw[];
+    const int d = H * HD;
+    const int row_elems = 2 * d;
+    const uint32_t stage_bytes = (uint32_t)DA_WARPS * row_elems * sizeof(T);
+    T* ring = reinterpret_cast<T*>(da_raw);
+    float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + DA_MAX_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)B * Tk;
+    const int64_t row_begin = (int64_t)blockIdx.x * R;
+    const int64_t row_end = min(total, row_begin + R);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            da_mbar_init(da_smem_u32(&full_bar[s]), 1);
+            da_mbar_init(da_smem_u32(&empty_bar[s]), DA_WARPS);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const int r_begin = chunk * DA_ROWS;
-    const int r_end = min(Tk, r_begin + DA_ROWS);
-    for (int r = r_begin + warp; r < r_end; r += DA_WARPS) {
-        const T* row = kvb + (int64_t)r * 2 * d;
-        float kf[DA_MAXSLOT][8], vf[DA_MAXSLOT][8];
+    __syncthreads();
+
+    if (warp == DA_WARPS) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t r = row_begin;
+            while (r < row_end) {
+                const int b = (int)(r / Tk);
+                const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
+                const T* src_clip = kv + (int64_t)b * kv_clip_stride;
+                for (int64_t r0 = r; r0 < seg_end; r0 += DA_WARPS) {
+                    const int nrows = (int)min((int64_t)DA_WARPS, seg_end - r0);
+                    da_mbar_wait(da_smem_u32(&empty_bar[stage]), phase ^ 1);
+                    const uint32_t bytes = (uint32_t)nrows * row_elems * sizeof(T);
+                    const uint32_t fb = da_smem_u32(&full_bar[stage]);
+                    da_mbar_expect_tx(fb, bytes);
+                    da_bulk_g2s(da_smem_u32(reinterpret_cast<unsigned char*>(ring) + (size_t)stage * stage_bytes),
+                                src_clip + (r0 - (int64_t)b * Tk) * row_elems, bytes, fb);
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                r = seg_end;
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers =====================
+    const int nslots = H * 8;
+    int stage = 0;
+    uint32_t phase = 0;
+    int64_t r = row_begin;
+    while (r < row_end) {
+        const int b = (int)(r / Tk);
+        const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
+        const T* qb = q + (int64_t)b * q_stride;
+        float qf[DA_MAXSLOT][8], of[DA_MAXSLOT][8], mrun[DA_MAXSLOT], lrun[DA_MAXSLOT];
+#pragma unroll
+        for (int s = 0; s < DA_MAXSLOT; ++s) {
+            const int slot = lane + 32 * s;
+            mrun[s] = -INFINITY;
+            lrun[s] = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { of[s][e] = 0.0f; qf[s][e] = 0.0f; }
+            if (slot < nslots) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) qf[s][e] = to_f32(qb[slot * 8 + e]);
+            }
+        }
+        for (int64_t r0 = r; r0 < seg_end; r0 += DA_WARPS) {
+            const int nrows = (int)min((int64_t)DA_WARPS, seg_end - r0);
+            da_mbar_wait(da_smem_u32(&full_bar[stage]), phase);
+            if (warp < nrows) {
+                const T* row = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)stage * stage_bytes) +
+                               (size_t)warp * row_elems;
+                // math is unconditional (idle slots carry zeros) so the shuffles stay warp-converged
+#pragma unroll
+                for (int s = 0; s < DA_MAXSLOT; ++s) {
+                    const int slot = lane + 32 * s;
+                    float kf[8], vf[8];
+                    if (slot < nslots) {
+                        Vec8<T>::load_shared(row + slot * 8, kf);
+                        Vec8<T>::load_shared(row + d + slot * 8, vf);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+                    }
+                    float dot = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) dot = fmaf(qf[s][e], kf[e], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    const float m_new = fmaxf(mrun[s], dot);
+                    const float sc = __expf(mrun[s] - m_new);     // exp(-inf) = 0 on the first row
+                    const float p = __expf(dot - m_new);
+                    lrun[s] = lrun[s] * sc + p;
+                    mrun[s] = m_new;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) of[s][e] = fmaf(p, vf[e], of[s][e] * sc);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) da_mbar_arrive(da_smem_u32(&empty_bar[stage]));
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        // ---- merge the 8 warps of this clip segment -> one partial record per head
 #pragma unroll
         for (int s = 0; s < DA_MAXSLOT; ++s) {
             const int slot = lane + 32 * s;
             if (slot < nslots) {
-                Vec8<T>::load(row + slot * 8, kf[s]);
-                Vec8<T>::load(row + d + slot * 8, vf[s]);
-            } else {
+                const int h = slot >> 3, e0 = (slot & 7) * 8;
+                float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
+                if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { kf[s][e] = 0.0f; vf[s][e] = 0.0f; }
+                for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
             }
         }
-        // math is unconditional (idle slots carry zeros) so the shuffles stay warp-converged
+        asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
+        float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
+        for (int i = threadIdx.x; i < H * HD; i += DA_WARPS * 32) {
+            const int h = i / HD, e = i % HD;
+            float m = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < DA_MAXSLOT; ++s) {
-            float dot = 0.0f;
+            for (int w = 0; w < DA_WARPS; ++w) m = fmaxf(m, merge[((size_t)w * H + h) * DA_PSTRIDE]);
+            float l = 0.0f, o = 0.0f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) dot = fmaf(qf[s][e], kf[s][e], dot);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-            const float m_new = fmaxf(mrun[s], dot);
-            const float sc = __expf(mrun[s] - m_new);     // exp(-inf) = 0 on the first row
-            const float p = __expf(dot - m_new);
-            lrun[s] = lrun[s] * sc + p;
-            mrun[s] = m_new;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) of[s][e] = fmaf(p, vf[s][e], of[s][e] * sc);
+            for (int w = 0; w < DA_WARPS; ++w) {
+                const float* rec = merge + ((size_t)w * H + h) * DA_PSTRIDE;
+                const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
+                l += rec[1] * sc;
+                o += rec[2 + e] * sc;
+            }
+            float* prec = prec_base + (size_t)h * DA_PSTRIDE;
+            if (e == 0) { prec[0] = m; prec[1] = l; }
+            prec[2 + e] = o;
         }
-    }
-    // per-warp records -> smem
-#pragma unroll
-    for (int s = 0; s < DA_MAXSLOT; ++s) {
-        const int slot = lane + 32 * s;
-        if (slot < nslots) {
-            const int h = slot >> 3, e0 = (slot & 7) * 8;
-            float* rec = da_smem + ((int64_t)warp * H + h) * DA_PSTRIDE;
-            if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
-        }
-    }
-    __syncthreads();
-    // merge the warps: thread -> (head, dim)
-    for (int i = threadIdx.x; i < H * HD; i += blockDim.x) {
-        const int h = i / HD, e = i % HD;
-        float m = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < DA_WARPS; ++w) m = fmaxf(m, da_smem[((int64_t)w * H + h) * DA_PSTRIDE]);
-        float l = 0.0f, o = 0.0f;
-#pragma unroll
-        for (int w = 0; w < DA_WARPS; ++w) {
-            const float* rec = da_smem + ((int64_t)w * H + h) * DA_PSTRIDE;
-            const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
-            l += rec[1] * sc;
-            o += rec[2 + e] * sc;
-        }
-        float* prec = partial + (((int64_t)b * nchunks + chunk) * H + h) * DA_PSTRIDE;
-        if (e == 0) { prec[0] = m; prec[1] = l; }
-        prec[2 + e] = o;
+        asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
+        r = seg_end;
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(HD)
-decode_attention_combine(const float* __restrict__ partial, int nchunks, int H, T* __restrict__ out) {
+decode_attention_combine(const float* __restrict__ partial, int Tk, int R, int H, T* __restrict__ out) {
     const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
+    const int c_first = (int)(((int64_t)b * Tk) / R), c_last = (int)((((int64_t)b + 1) * Tk - 1) / R);
     float m = -INFINITY;
-    for (int c = 0; c < nchunks; ++c) m = fmaxf(m, partial[(((int64_t)b * nchunks + c) * H + h) * DA_PSTRIDE]);
+    for (int c = c_first; c <= c_last; ++c) m = fmaxf(m, partial[((size_t)(c + b) * H + h) * DA_PSTRIDE]);
     float l = 0.0f, o = 0.0f;
-    for (int c = 0; c < nchunks; ++c) {
-        const float* rec = partial + (((int64_t)b * nchunks + c) * H + h) * DA_PSTRIDE;
+    for (int c = c_first; c <= c_last; ++c) {
+        const float* rec = partial + ((size_t)(c + b) * H + h) * DA_PSTRIDE;
         const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
         l += rec[1] * sc;
         o += rec[2 + e] * sc;
@@ -288,16 +398,32 @@ decode_attention_combine(const float* __restrict__ partial, int nchunks, int H, 
     out[(int64_t)b * H * HD + h * HD + e] = from_f32<T>(o / l);
 }
 
+static int g_da_sm_count = 0;
+size_t decode_attention_partial_floats(int B, int H) {
+    if (g_da_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_da_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_da_sm_count <= 0) g_da_sm_count = 148;
+    }
+    return (size_t)(g_da_sm_count + B) * H * DA_PSTRIDE;
+}
+
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial, T* out,
                       cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
-    const int nchunks = decode_attention_chunks(Tk);
-    const size_t smem = (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float);   // <= 42 KB
-    dim3 grid(nchunks, B);
+    (void)decode_attention_partial_floats(B, H);
+    const DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count);
+    static bool attr_set[2] = {false, false};
+    const int which = sizeof(T) == 4 ? 0 : 1;
+    if (!attr_set[which]) {
+        cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_set[which] = true;
+    }
     if (ev0) cudaEventRecord(ev0, st);
-    decode_attention_partial<T><<<grid, DA_WARPS * 32, smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, H, partial);
+    decode_attention_stream<T><<<p.G, DA_THREADS, p.smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, B, H, p.R, p.stages, partial);
     if (ev1) cudaEventRecord(ev1, st);
-    decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, nchunks, H, out);
+    decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, Tk, p.R, H, out);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, int, int, float*, float*, cudaStream_t,
                                       cudaEvent_t, cudaEvent_t);

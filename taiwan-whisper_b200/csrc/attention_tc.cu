@@ -1,0 +1,370 @@
+// Encoder self-attention on 5th-gen tensor cores (sm_100a): softmax(Q K^T) V per (clip, head), non-causal,
+// head_dim 64, bf16 operands, fp32 accumulate / softmax.  (HF WhisperAttention.forward,
+// modeling_whisper.py:284-358; q is pre-scaled, no mask.)
+//
+// One CTA = one 128-query block of one (clip, head); two CTAs are co-resident per SM (256 TMEM columns,
+// ~112 KB shared memory each) so one CTA's softmax overlaps the other's MMAs.
+//   warp 4      TMA producer: Q tile once, then K / V tiles (128 keys x 64 dims, 128-byte swizzle) through
+//               2-deep rings, straight out of the fused QKV activation matrix [B*S, 3d]
+//   warp 5      MMA issuer: S = Q K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) into TMEM columns
+//               [0,128); O_tile = P V (M128 N64 K16 x8, A = P from shared memory, B = V tile used MN-major)
+//               into TMEM columns [128,192)
+//   warps 0-3   softmax: thread = query row.  tcgen05.ld the scores, running max / sum in registers (no
+//               shuffles: a thread owns its row), P = exp2(s*log2e - m*log2e) rounded to bf16 and written to
+//               shared memory in the K-major 128-byte-swizzle layout the MMA expects, then O_reg = O_reg*scale
+//               + O_tile read back from TMEM.  Final O / l stored as bf16 (128 contiguous bytes per row).
+// Keys beyond the clip length (the 1536-padded tail, which TMA fills with the next clip's rows or zeros)
+// are masked to -inf before the softmax.
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace tw {
+
+constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64;
+constexpr int FA_THREADS = 192;
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;      // one 128 x 64 bf16 tile = 16 KB
+constexpr int FA_SMEM = 1024 + FA_TILE_BYTES * (1 + 2 + 1 + 2) + 256;   // Q, K x2, V x1, P (2 atoms): 2 CTAs / SM
+constexpr int FA_TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t fa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fa_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fa_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fa_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fa_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FA_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FA_WAIT_DONE;\n"
+        "bra FA_WAIT_LOOP;\n"
+        "FA_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fa_tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fa_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fa_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fa_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fa_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptors, 128-byte swizzle, 8-row groups 1024 B apart (SBO); version 1 (sm_100)
+__device__ __forceinline__ uint64_t fa_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: f32 accumulate, bf16 x bf16; b_mn_major selects an MN-major B operand (bit 16)
+__host__ __device__ constexpr uint32_t fa_idesc(int M, int N, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int S, int H) {
+    extern __shared__ unsigned char fa_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;
+    unsigned char* sK = smem + FA_TILE_BYTES;           // 2 stages
+    unsigned char* sV = smem + 3 * FA_TILE_BYTES;       // 1 stage (V(j) is only needed after softmax(j))
+    unsigned char* sP = smem + 4 * FA_TILE_BYTES;       // 2 swizzle atoms (keys 0-63 | 64-127), 128 rows each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE_BYTES);
+    uint64_t* q_full = bars;          // 1
+    uint64_t* k_full = bars + 1;      // 2
+    uint64_t* k_empty = bars + 3;     // 2
+    uint64_t* v_full = bars + 5;      // 2
+    uint64_t* v_empty = bars + 7;     // 2
+    uint64_t* s_full = bars + 9;      // 1  QK^T done
+    uint64_t* p_full = bars + 10;     // 1  P written (and S consumed)
+    uint64_t* o_full = bars + 11;     // 1  PV done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int d = H * FA_D;
+    const int q0 = qb * FA_BQ;
+    const int n_tiles = (S + FA_BK - 1) / FA_BK;
+    const int row_base = b * S;                       // first row of this clip in the [B*S, 3d] matrix
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        fa_mbar_init(fa_smem_u32(q_full), 1);
+        for (int i = 0; i < 2; ++i) {
+            fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&k_empty[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_empty[i]), 1);
+        }
+        fa_mbar_init(fa_smem_u32(s_full), 1);
+        fa_mbar_init(fa_smem_u32(p_full), 4);          // one arrive per softmax warp
+        fa_mbar_init(fa_smem_u32(o_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fa_smem_u32(tmem_ptr)), "r"(FA_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fa_fence_before();
+    __syncthreads();
+    fa_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_S = tmem_base;            // columns [0,128)
+    const uint32_t tmem_O = tmem_base + 128;      // columns [128,192)
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
+            fa_tma_load_2d(&map_qkv, fa_smem_u32(q_full), fa_smem_u32(sQ), h * FA_D, row_base + q0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
+                fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
+                fa_tma_load_2d(&map_qkv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), d + h * FA_D,
+                               row_base + j * FA_BK);
+                fa_mbar_wait(fa_smem_u32(&v_empty[0]), (j & 1) ^ 1);
+                fa_mbar_expect_tx(fa_smem_u32(&v_full[0]), FA_TILE_BYTES);
+                fa_tma_load_2d(&map_qkv, fa_smem_u32(&v_full[0]), fa_smem_u32(sV), 2 * d + h * FA_D, row_base + j * FA_BK);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
+            constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
+            const uint64_t q_desc = fa_desc(fa_smem_u32(sQ));
+            fa_mbar_wait(fa_smem_u32(q_full), 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                // S(j) = Q K(j)^T   (S columns are free: the softmax warps arrived on p_full(j-1))
+                fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
+                if (j > 0) fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
+                fa_fence_after();
+                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+                fa_commit(fa_smem_u32(&k_empty[st]));
+                fa_commit(fa_smem_u32(s_full));
+                if (j > 0) {
+                    // O_tile(j-1) = P(j-1) V(j-1): P is in shared memory since p_full(j-1)
+                    fa_mbar_wait(fa_smem_u32(&v_full[0]), (j - 1) & 1);
+                    fa_fence_after();
+                    const uint32_t v_addr = fa_smem_u32(sV);
+#pragma unroll
+                    for (int k = 0; k < FA_BK / 16; ++k) {
+                        // A: P atom (k/4), 32-byte steps inside the 128-byte swizzle row; B: 16 key rows = 2048 bytes
+                        const uint64_t p_desc = fa_desc(fa_smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2 * (k & 3);
+                        const uint64_t v_desc = fa_desc(v_addr + k * 2048);
+                        fa_mma(tmem_O, p_desc, v_desc, idesc_pv, k > 0 ? 1u : 0u);
+                    }
+                    fa_commit(fa_smem_u32(&v_empty[0]));
+                    fa_commit(fa_smem_u32(o_full));
+                }
+            }
+            {   // last P V
+                const int j = n_tiles;
+                fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
+                fa_mbar_wait(fa_smem_u32(&v_full[0]), (j - 1) & 1);
+                fa_fence_after();
+                const uint32_t v_addr = fa_smem_u32(sV);
+#pragma unroll
+                for (int k = 0; k < FA_BK / 16; ++k) {
+                    const uint64_t p_desc = fa_desc(fa_smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2 * (k & 3);
+                    const uint64_t v_desc = fa_desc(v_addr + k * 2048);
+                    fa_mma(tmem_O, p_desc, v_desc, idesc_pv, k > 0 ? 1u : 0u);
+                }
+                fa_commit(fa_smem_u32(&v_empty[0]));
+                fa_commit(fa_smem_u32(o_full));
+            }
+        }
+    } else {
+        // ===================== softmax warps 0..3: thread = query row =====================
+        const int r = warp * 32 + lane;                 // row inside the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const float LOG2E = 1.4426950408889634f;
+        float o_acc[FA_D];
+#pragma unroll
+        for (int i = 0; i < FA_D; ++i) o_acc[i] = 0.0f;
+        float m_run = -INFINITY, l_run = 0.0f, scale_prev = 1.0f;
+        for (int j = 0; j < n_tiles; ++j) {
+            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
+            fa_fence_after();
+            const int valid = S - j * FA_BK;            // keys >= valid are padding
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < FA_BK; c += 32) {
+                uint32_t v[32];
+                fa_tmem_ld32(tmem_S + lane_off + c, v);
+                fa_tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float s = (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float scale = exp2f((m_run - m_new) * LOG2E);     // 0 on the first tile (m_run = -inf)
+            const float mneg = -m_new * LOG2E;
+            // the previous P V must have finished reading P before it is overwritten, and O_tile(j-1) is folded in
+            if (j > 0) {
+                fa_mbar_wait(fa_smem_u32(o_full), (j - 1) & 1);
+                fa_fence_after();
+#pragma unroll
+                for (int c = 0; c < FA_D; c += 32) {
+                    uint32_t v[32];
+                    fa_tmem_ld32(tmem_O + lane_off + c, v);
+                    fa_tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], scale_prev, __uint_as_float(v[i]));
+                }
+            }
+            // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> shared memory (K-major, 128-byte swizzle)
+            float lsum = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < FA_BK; c += 32) {
+                uint32_t v[32];
+                fa_tmem_ld32(tmem_S + lane_off + c, v);
+                fa_tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = (c + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), LOG2E, mneg)) : 0.0f;
+                    const float p1 = (c + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)) : 0.0f;
+                    lsum += p0 + p1;
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+                // 32 keys = 64 bytes = 4 chunks of 16 B; chunk index inside the 128-byte row: ((c % 64) / 8) + q
+                unsigned char* prow = sP + (c >> 6) * FA_TILE_BYTES + r * 128;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int chunk = ((c & 63) >> 3) + qd;
+                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+                }
+            }
+            l_run = l_run * scale + lsum;
+            m_run = m_new;
+            scale_prev = scale;
+            // P visible to the tensor core (async proxy); S columns free again
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fa_fence_before();
+            __syncwarp();
+            if (lane == 0) fa_mbar_arrive(fa_smem_u32(p_full));
+        }
+        // last O tile.  NB: scale_prev belongs to the tile whose P V is now finishing: O = O*scale + O_tile
+        fa_mbar_wait(fa_smem_u32(o_full), (n_tiles - 1) & 1);
+        fa_fence_after();
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t v[32];
+            fa_tmem_ld32(tmem_O + lane_off + c, v);
+            fa_tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], scale_prev, __uint_as_float(v[i]));
+        }
+        const int q = q0 + r;
+        if (q < S) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* orow = out + ((int64_t)(row_base + q)) * d + h * FA_D;
+#pragma unroll
+            for (int i = 0; i < FA_D; i += 8) {
+                uint4 pk;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(orow + i) = pk;
+            }
+        }
+        fa_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        fa_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host ----------------------------------------------------------------------------------
+typedef CUresult (*FaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static FaEncodeTiledFn g_fa_encode = nullptr;
+
+int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st) {
+    if (!g_fa_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            ctx->set_error(TW_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+            return TW_E_CUDA;
+        }
+        g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    }
+    const int d = H * FA_D;
+    if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (d % 8)) {
+        ctx->set_error(TW_E_UNSUPPORTED, "encoder_attention_tc: qkv must be 16-byte aligned");
+        return TW_E_UNSUPPORTED;
+    }
+    static const void* cached_ptr = nullptr;
+    static int cached_rows = 0, cached_cols = 0;
+    static CUtensorMap cached_map;
+    const int rows = B * S, cols = 3 * d;
+    if (cached_ptr != qkv || cached_rows != rows || cached_cols != cols) {
+        const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+        const cuuint32_t box[2] = {64, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_fa_encode(&cached_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(qkv), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ctx->set_error(TW_E_CUDA, "encoder_attention_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+            return TW_E_CUDA;
+        }
+        cached_ptr = qkv; cached_rows = rows; cached_cols = cols;
+    }
+    dim3 grid(ceil_div(S, FA_BQ), H, B);
+    encoder_attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+}  // namespace tw

@@ -60,12 +60,14 @@ void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 // encoder self-attention on qkv T [B*S, 3d] (q pre-scaled), S keys per clip, out T [B*S, d]
 template <typename T>
 void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStream_t st);
+// tcgen05 flash attention (attention_tc.cu), bf16 only
+int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st);
 // decode attention (1 query per clip) over kv rows [Tk][2d] (K|V), clip stride kv_clip_stride elements.
-// q T [B, q_stride]; partial workspace f32 [B * nchunks * H * 66]; out T [B, d].
+// q T [B, q_stride]; partial workspace f32 [decode_attention_partial_floats]; out T [B, d].
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial,
                       T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
-int decode_attention_chunks(int Tk);
+size_t decode_attention_partial_floats(int B, int H);   // size of the partial workspace
 
 // ---- token selection (select.cu)
 struct RulesDev {

@@ -80,6 +80,7 @@ struct tw_model {
     tw_model_desc desc{};
     int esz = 2;                 // bytes per element of the model dtype
     bool use_tc = false;         // tcgen05 GEMMs (bf16 only)
+    bool use_tc_attn = false;    // tcgen05 encoder attention (bf16 only)
     std::vector<void*> allocs;
     size_t bytes = 0;
     // weights
@@ -290,7 +291,7 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, &m->dq, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dhmid, B * D.ffn * e));
     TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * D.vocab * sizeof(float)));
-    TW_CHECK(dev_alloc(m, (void**)&m->dpartial, B * decode_attention_chunks(TW_N_CTX) * D.heads * 66 * sizeof(float)));
+    TW_CHECK(dev_alloc(m, (void**)&m->dpartial, decode_attention_partial_floats((int)B, D.heads) * sizeof(float)));
     TW_CHECK(dev_alloc(m, (void**)&m->dstate, (6 * B + 4) * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
     TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
@@ -322,6 +323,20 @@ int gemm<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* A, int64_t lda, const 
     return TW_OK;
 }
 
+template <typename T>
+int enc_attention(tw_model* m, const T* qkv, T* att, int B, cudaStream_t st);
+template <>
+int enc_attention<float>(tw_model* m, const float* qkv, float* att, int B, cudaStream_t st) {
+    encoder_attention_simt<float>(qkv, att, B, TW_N_CTX, m->desc.heads, st);
+    return TW_OK;
+}
+template <>
+int enc_attention<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* qkv, __nv_bfloat16* att, int B, cudaStream_t st) {
+    if (m->use_tc_attn) return encoder_attention_tc(m->ctx, qkv, att, B, TW_N_CTX, m->desc.heads, st);
+    encoder_attention_simt<__nv_bfloat16>(qkv, att, B, TW_N_CTX, m->desc.heads, st);
+    return TW_OK;
+}
+
 inline GemmEpi mk_epi(int mode, const float* bias, void* C, int64_t ldc, const float* pos = nullptr, int period = 1) {
     GemmEpi e;
     e.mode = mode; e.bias = bias; e.C = C; e.ldc = ldc; e.pos = pos; e.pos_period = period;
@@ -347,7 +362,7 @@ int encode_impl(tw_model* m, const float* mel, int B, void* enc_out, int tap_lay
         const LayerW& L = m->enc[l];
         layernorm<T>(x, L.ln1_g, L.ln1_b, xn, M, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, M, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
-        encoder_attention_simt<T>(qkv, att, B, TW_N_CTX, D.heads, st);
+        TW_CHECK(enc_attention<T>(m, qkv, att, B, st));
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, M, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         layernorm<T>(x, L.ln3_g, L.ln3_b, xn, M, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, M, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
@@ -570,6 +585,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->esz = D.dtype == TW_BF16 ? 2 : 4;
     const char* g = getenv("TWB200_GEMM");
     m->use_tc = (D.dtype == TW_BF16) && !(g && strcmp(g, "simt") == 0);
+    const char* ga = getenv("TWB200_ATTN");
+    m->use_tc_attn = (D.dtype == TW_BF16) && !(ga && strcmp(ga, "simt") == 0);
     WeightTable wt;
     for (size_t i = 0; i < n; ++i)
         if (table[i].name) wt.by_name[table[i].name] = &table[i];
@@ -708,6 +725,44 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
         ctx->set_error(TW_E_INVALID, "tw_debug_gemm: dtype");
         return TW_E_INVALID;
     }
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride, int Tk, int B,
+                              int H, int dtype, void* out, void* stream) {
+    if (!ctx || !q || !kv || !out || B <= 0 || Tk <= 0 || H <= 0 || H > 20) return TW_E_INVALID;
+    static float* scratch = nullptr;
+    static size_t scratch_floats = 0;
+    const size_t need = decode_attention_partial_floats(B, H);
+    if (need > scratch_floats) {
+        if (scratch) cudaFree(scratch);
+        TW_CUDA_OK(ctx, cudaMalloc(&scratch, need * sizeof(float)));
+        scratch_floats = need;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TW_BF16)
+        decode_attention<__nv_bfloat16>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)kv, kv_clip_stride, Tk, B, H, scratch,
+                                        (__nv_bfloat16*)out, st);
+    else
+        decode_attention<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, B, H, scratch, (float*)out, st);
+    ctx->launches += 2;
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_debug_encoder_attention(tw_ctx* ctx, const void* qkv, void* out, int B, int S, int H, int dtype, int impl, void* stream) {
+    if (!ctx || !qkv || !out || B <= 0 || S <= 0 || H <= 0) return TW_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TW_BF16 && impl == 1) {
+        ctx->launches += 1;
+        return encoder_attention_tc(ctx, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, B, S, H, st);
+    }
+    if (dtype == TW_BF16)
+        encoder_attention_simt<__nv_bfloat16>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, B, S, H, st);
+    else
+        encoder_attention_simt<float>((const float*)qkv, (float*)out, B, S, H, st);
+    ctx->launches += 1;
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

@@ -125,6 +125,57 @@ def test_gemm_fp32_check_mode_vs_torch():
         assert (out - ref).abs().max().item() < 1e-4
 
 
+# ------------------------------------------------------------------------------------------ attention kernels
+def _attn_ref(qkv, B, S, H):
+    d = H * 64
+    x = qkv.float().view(B, S, 3, H, 64)
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2), -1)
+    return (p @ v).transpose(1, 2).reshape(B * S, d)
+
+
+@pytest.mark.parametrize("B,S,H", [(2, 1500, 6), (1, 128, 2), (3, 200, 2), (1, 1500, 20)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_encoder_attention_kernels_vs_torch(B, S, H, impl):
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + S + H)
+    qkv = torch.randn((B * S, 3 * d), device="cuda", generator=g)
+    qkv[:, :d] *= 0.3          # q is pre-scaled on the real path
+    qkv = qkv.bfloat16()
+    out = torch.zeros((B * S, d), device="cuda", dtype=torch.bfloat16)
+    ctx.check(ctx.lib.tw_debug_encoder_attention(ctx.handle, qkv.data_ptr(), out.data_ptr(), B, S, H, twlib.TW_BF16, impl,
+                                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, B, S, H)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err                       # bf16 P and bf16 output rounding
+
+
+@pytest.mark.parametrize("Tk,B,H", [(1500, 3, 6), (1, 2, 2), (37, 5, 20), (448, 64, 2)])
+def test_decode_attention_kernel_vs_torch(Tk, B, H):
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(Tk + B + H)
+    for dt, tw_dt, tol in ((torch.float32, twlib.TW_F32, 1e-4), (torch.bfloat16, twlib.TW_BF16, 1e-2)):
+        stride = (Tk + 3) * 2 * d                    # clip stride larger than Tk rows (as the self-attention cache has)
+        kv = torch.randn((B, Tk + 3, 2 * d), device="cuda", generator=g).to(dt)
+        q = (torch.randn((B, d), device="cuda", generator=g) * 0.3).to(dt)
+        out = torch.zeros((B, d), device="cuda", dtype=dt)
+        ctx.check(ctx.lib.tw_debug_decode_attention(ctx.handle, q.data_ptr(), d, kv.data_ptr(), stride, Tk, B, H, tw_dt,
+                                                    out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        x = kv[:, :Tk].float().view(B, Tk, 2, H, 64)
+        sc = torch.einsum("bhd,bthd->bht", q.float().view(B, H, 64), x[:, :, 0])
+        ref = torch.einsum("bht,bthd->bhd", torch.softmax(sc, -1), x[:, :, 1]).reshape(B, d)
+        err = (out.float() - ref).abs().max().item()
+        assert err < tol, (dt, err)
+
+
 # ------------------------------------------------------------------------------------------ encoder
 @pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
 def test_encoder_fp32_check_mode(shape_name):
