@@ -26,6 +26,11 @@ struct GemmEpi {
     int64_t ldc = 0;
     const float* pos = nullptr;   // [pos_period, N] f32 (EPI_GELU_POS)
     int pos_period = 1;
+    // column split of the store epilogues (skinny kernel only): columns >= n_split go to C2[m*ldc2 + n - n_split]
+    // (the fused QKV projection writes K|V straight into the self-attention cache row of this position)
+    int n_split = 0x7fffffff;
+    void* C2 = nullptr;
+    int64_t ldc2 = 0;
 };
 
 // CUDA-core FMA GEMM, fp32 accumulate in a fixed order; the fp32 check-mode path (T = float)
@@ -38,6 +43,11 @@ void gemm_simt(const T* A, int64_t lda, const T* W, int64_t ldw, int M, int N, i
 int gemm_tc_init(tw_ctx* ctx);
 int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
             const GemmEpi& epi, cudaStream_t st);
+
+// skinny (M <= 64) weight-streaming GEMM for the decode steps (gemm_skinny.cu), bf16
+bool gemm_skinny_supported(int M, int N, int K, const GemmEpi& epi);
+int gemm_skinny(tw_ctx* ctx, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
+                const GemmEpi& epi, cudaStream_t st);
 
 // ---- elementwise / normalisation (elementwise.cu)
 template <typename T>

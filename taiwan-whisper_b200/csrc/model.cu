@@ -81,6 +81,7 @@ struct tw_model {
     int esz = 2;                 // bytes per element of the model dtype
     bool use_tc = false;         // tcgen05 GEMMs (bf16 only)
     bool use_tc_attn = false;    // tcgen05 encoder attention (bf16 only)
+    bool use_skinny = false;     // weight-streaming skinny GEMM for decode steps (bf16 only)
     std::vector<void*> allocs;
     size_t bytes = 0;
     // weights
@@ -318,6 +319,7 @@ template <>
 int gemm<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
                         const GemmEpi& epi, cudaStream_t st) {
     m->ctx->launches += 1;
+    if (m->use_tc && m->use_skinny && gemm_skinny_supported(M, N, K, epi)) return gemm_skinny(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     if (m->use_tc) return gemm_tc(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     gemm_simt<__nv_bfloat16>(A, lda, W, ldw, M, N, K, epi, st);
     return TW_OK;
@@ -450,8 +452,15 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
             const LayerW& L = m->dec[l];
             T* cache = (T*)m->self_kv + l * self_layer;
             layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
-            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
-            kv_append<T>(qkv, cache, pos, B, d, D.max_target, st);
+            GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d);
+            const bool fused_append = sizeof(T) == 2 && m->use_tc && m->use_skinny && gemm_skinny_supported(B, 3 * d, d, qe);
+            if (fused_append) {                      // K|V columns land directly in the cache row of this position
+                qe.n_split = d;
+                qe.C2 = cache + (size_t)pos * 2 * d;
+                qe.ldc2 = (int64_t)D.max_target * 2 * d;
+            }
+            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
+            if (!fused_append) kv_append<T>(qkv, cache, pos, B, d, D.max_target, st);
             decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, pos + 1, B, H, m->dpartial, att, st);
             TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
             layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
@@ -587,6 +596,10 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_tc = (D.dtype == TW_BF16) && !(g && strcmp(g, "simt") == 0);
     const char* ga = getenv("TWB200_ATTN");
     m->use_tc_attn = (D.dtype == TW_BF16) && !(ga && strcmp(ga, "simt") == 0);
+    const char* gs = getenv("TWB200_SKINNY");
+    // measured on B200 (profiles/r01_decode_kernels_ncu.md): the tcgen05 N=32-tile kernel beats the mma.sync skinny
+    // kernel at every decode shape, so the skinny kernel is opt-in (TWB200_SKINNY=1) until it is reworked
+    m->use_skinny = m->use_tc && (gs && strcmp(gs, "1") == 0);
     WeightTable wt;
     for (size_t i = 0; i < n; ++i)
         if (table[i].name) wt.by_name[table[i].name] = &table[i];
@@ -719,6 +732,7 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
     if (dtype == TW_F32) {
         gemm_simt<float>((const float*)A, K, (const float*)W, K, M, N, K, e, st);
     } else if (dtype == TW_BF16) {
+        if (use_tc == 2) return gemm_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         if (use_tc) return gemm_tc(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         gemm_simt<__nv_bfloat16>((const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
     } else {

@@ -54,6 +54,6 @@ def gemm_debug(A, W, bias, mode, use_tc, out_dtype=None, C_init=None, pos=None, 
         Cc = C_init.clone() if C_init is not None else torch.zeros((M, N), dtype=torch.float32, device=A.device)
     ctx.check(ctx.lib.tw_debug_gemm(ctx.handle, A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
                                     Cc.data_ptr(), M, N, K, dt, mode, pos.data_ptr() if pos is not None else None, period,
-                                    1 if use_tc else 0, torch.cuda.current_stream().cuda_stream))
+                                    int(use_tc), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return Cc

@@ -89,6 +89,40 @@ def bench_encoder_attention():
         print(f"encoder_attention({name}) B={B}: {ms:.2f} ms  {fl/ms/1e9:.1f} TFLOP/s")
 
 
+def bench_small_for_ncu():
+    """A handful of launches of the decode-side kernels at large-v3 / B=64 shapes, for
+    `ncu --metrics gpu__time_duration.sum` (per-launch device time without host overhead)."""
+    B, d, H, ffn = 64, 1280, 20, 5120
+    x = (torch.randn((B, d), device=dev) * 0.5).bfloat16()
+    for (N, K) in ((3840, 1280), (1280, 1280), (5120, 1280), (1280, 5120), (51866, 1280)):
+        A = (torch.randn((B, K), device=dev) * 0.5).bfloat16()
+        W = (torch.randn((N, K), device=dev) * 0.05).bfloat16()
+        Cc = torch.empty((B, N), device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ctx.check(ctx.lib.tw_debug_gemm(ctx.handle, A.data_ptr(), W.data_ptr(), None, Cc.data_ptr(), B, N, K, twlib.TW_BF16, 0,
+                                            None, 1, 1, st()))
+        Cf = torch.zeros((B, N), device=dev)
+        for mode, C_ in ((0, Cc), (2, Cf)):
+            if K > 1280 and mode != 2:
+                continue
+            for _ in range(3):
+                ctx.check(ctx.lib.tw_debug_gemm(ctx.handle, A.data_ptr(), W.data_ptr(), None, C_.data_ptr(), B, N, K, twlib.TW_BF16,
+                                                mode, None, 1, 2, st()))
+    for Tk in (8, 128, 256, 1500):
+        kv = torch.randn((B, Tk, 2 * d), device=dev).bfloat16()
+        q = torch.randn((B, d), device=dev).bfloat16() * 0.125
+        out = torch.empty((B, d), device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            ctx.check(ctx.lib.tw_debug_decode_attention(ctx.handle, q.data_ptr(), d, kv.data_ptr(), Tk * 2 * d, Tk, B, H,
+                                                        twlib.TW_BF16, out.data_ptr(), st()))
+    torch.cuda.synchronize()
+    print("small done")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "small_for_ncu":
+    bench_small_for_ncu()
+    sys.exit(0)
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["decode_attention", "gemm", "encoder_attention"]
     for w in what:
