@@ -244,9 +244,9 @@ def main():
     for i in range(K):
         outs.append(step_device(W + i))
     if world > 1:       # final result gather (the only collective of the path)
-        toks = torch.cat([o[0] for o in outs])
-        gathered = [torch.empty_like(toks) for _ in range(world)]
-        dist.all_gather(gathered, toks)
+        from taiwan_whisper_b200.shard import gather_token_rows
+        all_toks, all_lens = gather_token_rows(torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs]),
+                                               model._rules(False)["pad"], world * K * B)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
