@@ -209,6 +209,14 @@ template <> struct Vec8<__nv_bfloat16> {
     }
 };
 
+// rows per CTA for a stream of total_rows split over at most `grid` CTAs (same formula on host and device)
+__host__ __device__ inline int da_rows_per_cta(int64_t total_rows, int grid) {
+    int64_t g = (total_rows + DA_WARPS - 1) / DA_WARPS;
+    if (g > grid) g = grid;
+    if (g < 1) g = 1;
+    return (int)((total_rows + g - 1) / g);
+}
+
 struct DaPlan {
     int G;        // CTAs
     int R;        // rows per CTA
@@ -234,8 +242,8 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count) {
 
 template <typename T>
 __global__ void __launch_bounds__(DA_THREADS, 1)
-decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk, int B,
-                        int H, int R, int stages, float* __restrict__ partial) {
+decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
+                        const int32_t* __restrict__ d_tk, int B, int H, int stages, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
     const int row_elems = 2 * d;
@@ -247,9 +255,12 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d_tk) Tk = *d_tk + 1;
     const int64_t total = (int64_t)B * Tk;
+    const int R = da_rows_per_cta(total, gridDim.x);
     const int64_t row_begin = (int64_t)blockIdx.x * R;
     const int64_t row_end = min(total, row_begin + R);
+    if (row_begin >= total) return;             // short caches do not need every CTA
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -383,8 +394,11 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
 
 template <typename T>
 __global__ void __launch_bounds__(HD)
-decode_attention_combine(const float* __restrict__ partial, int Tk, int R, int H, T* __restrict__ out) {
+decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_t* __restrict__ d_tk, int B, int grid, int H,
+                         T* __restrict__ out) {
     const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
+    if (d_tk) Tk = *d_tk + 1;
+    const int R = da_rows_per_cta((int64_t)B * Tk, grid);
     const int c_first = (int)(((int64_t)b * Tk) / R), c_last = (int)((((int64_t)b + 1) * Tk - 1) / R);
     float m = -INFINITY;
     for (int c = c_first; c <= c_last; ++c) m = fmaxf(m, partial[((size_t)(c + b) * H + h) * DA_PSTRIDE]);
@@ -410,10 +424,11 @@ size_t decode_attention_partial_floats(int B, int H) {
 }
 
 template <typename T>
-void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial, T* out,
-                      cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     (void)decode_attention_partial_floats(B, H);
-    const DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count);
+    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count);
+    if (d_tk) p.G = g_da_sm_count;               // row count only known on the device: launch every CTA
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
@@ -421,13 +436,13 @@ void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip
         attr_set[which] = true;
     }
     if (ev0) cudaEventRecord(ev0, st);
-    decode_attention_stream<T><<<p.G, DA_THREADS, p.smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, B, H, p.R, p.stages, partial);
+    decode_attention_stream<T><<<p.G, DA_THREADS, p.smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H, p.stages, partial);
     if (ev1) cudaEventRecord(ev1, st);
-    decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, Tk, p.R, H, out);
+    decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, Tk, d_tk, B, p.G, H, out);
 }
-template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, int, int, float*, float*, cudaStream_t,
-                                      cudaEvent_t, cudaEvent_t);
-template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, int, int, float*,
-                                              __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
+template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
+                                      cudaStream_t, cudaEvent_t, cudaEvent_t);
+template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*, int, int,
+                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
 
 }  // namespace tw

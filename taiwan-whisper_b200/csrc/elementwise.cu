@@ -145,35 +145,41 @@ template void im2col_conv2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, 
 
 // ---- decoder input: x[b] = E[tok[b]] + P[pos]  (HF WhisperDecoder.forward :738-760)
 template <typename T>
-__global__ void embed_kernel(const int32_t* __restrict__ tok, const T* __restrict__ E, const T* __restrict__ P, int pos,
-                             float* __restrict__ x, int d) {
+__global__ void embed_kernel(const int32_t* __restrict__ tok, const T* __restrict__ E, const T* __restrict__ P,
+                             const int32_t* __restrict__ d_step, float* __restrict__ x, int d) {
     const int b = blockIdx.x;
     const int t = tok[b];
+    const int pos = d_step[0];
     for (int i = threadIdx.x; i < d; i += blockDim.x)
         x[(int64_t)b * d + i] = to_f32(E[(int64_t)t * d + i]) + to_f32(P[(int64_t)pos * d + i]);
 }
 template <typename T>
-void embed_tokens(const int32_t* tok, const T* E, const T* P, int pos, float* x, int B, int d, cudaStream_t st) {
-    embed_kernel<T><<<B, 256, 0, st>>>(tok, E, P, pos, x, d);
+void embed_tokens(const int32_t* tok, const T* E, const T* P, const int32_t* d_step, float* x, int B, int d, cudaStream_t st) {
+    embed_kernel<T><<<B, 256, 0, st>>>(tok, E, P, d_step, x, d);
 }
-template void embed_tokens<float>(const int32_t*, const float*, const float*, int, float*, int, int, cudaStream_t);
-template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, int, float*, int, int,
+template void embed_tokens<float>(const int32_t*, const float*, const float*, const int32_t*, float*, int, int, cudaStream_t);
+template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, const int32_t*, float*, int, int,
                                           cudaStream_t);
 
 // ---- self-attention KV cache append: cache[b][pos][0:2d] = qkv[b][d:3d]
 template <typename T>
-__global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, int pos, int d, int max_len) {
+__global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ d_step, int d,
+                                 int max_len) {
     const int b = blockIdx.x;
+    const int pos = d_step[0];
     const T* src = qkv + (int64_t)b * 3 * d + d;
     T* dst = cache + ((int64_t)b * max_len + pos) * 2 * d;
     for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) dst[i] = src[i];
 }
 template <typename T>
-void kv_append(const T* qkv, T* cache, int pos, int B, int d, int max_len, cudaStream_t st) {
-    kv_append_kernel<T><<<B, 256, 0, st>>>(qkv, cache, pos, d, max_len);
+void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st) {
+    kv_append_kernel<T><<<B, 256, 0, st>>>(qkv, cache, d_step, d, max_len);
 }
-template void kv_append<float>(const float*, float*, int, int, int, int, cudaStream_t);
-template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t);
+template void kv_append<float>(const float*, float*, const int32_t*, int, int, int, cudaStream_t);
+template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const int32_t*, int, int, int, cudaStream_t);
+
+__global__ void advance_step_kernel(int32_t* d_step) { d_step[0] += 1; }
+void advance_step(int32_t* d_step, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(d_step); }
 
 __global__ void copy_f32_kernel(const float4* __restrict__ s, float4* __restrict__ d, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];

@@ -104,7 +104,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K, GemmEpi epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K, int ksplit,
+               GemmEpi epi) {
     using Cfg = TcCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
@@ -118,8 +119,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
-    const int k_blocks = (K + TC_BK - 1) / TC_BK;
+    // a work item = (output tile, K split): split-K (ksplit > 1) is used by the residual-add epilogue of the skinny
+    // decode GEMMs, whose partial sums are combined with fp32 atomics
+    const int num_tiles = tiles_m * tiles_n * ksplit;
+    const int k_blocks_total = (K + TC_BK - 1) / TC_BK;
+    const int kb_per_split = (k_blocks_total + ksplit - 1) / ksplit;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -150,8 +154,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int ks = tile % ksplit, mn = tile / ksplit;
+                const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
+                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -175,7 +181,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < k_blocks; ++kb) {
+                const int ks = tile % ksplit;
+                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -184,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -197,7 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+            const int ks = tile % ksplit, mn = tile / ksplit;
+            const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
@@ -217,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const bool full = (n0 + 32 <= N);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                if (epi.bias) {
+                if (epi.bias && ks == 0) {
                     if (full) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -253,7 +262,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 } else {
                     float* cp = reinterpret_cast<float*>(epi.C) + o;
                     const bool vec = full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
-                    if (epi.mode == EPI_RESID) {
+                    if (epi.mode == EPI_RESID && ksplit > 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (n0 + j < N) atomicAdd(cp + j, v[j]);
+                    } else if (epi.mode == EPI_RESID) {
                         if (vec) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -361,14 +373,24 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     CUtensorMap ma, mw;
     TW_CHECK(get_map(ctx, A, M, K, lda, TC_BM, &ma));
     TW_CHECK(get_map(ctx, W, N, K, ldw, BN, &mw));
-    const int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+    int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+    int ksplit = 1;
+    if (BN == 32 && epi.mode == EPI_RESID) {
+        // skinny residual GEMM: split K so that ~one wave of CTAs each streams a short K range
+        const int kb = ceil_div(K, TC_BK);
+        ksplit = g_sm_count / tiles;
+        if (ksplit > kb / 4) ksplit = kb / 4;
+        if (ksplit < 1) ksplit = 1;
+        ksplit = ceil_div(kb, ceil_div(kb, ksplit));        // every split gets at least one K block
+    }
+    tiles *= ksplit;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
     if (BN == 256)
-        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
     else if (BN == 32)
-        gemm_tc_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+        gemm_tc_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
     else
-        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(ma, mw, M, N, K, epi);
+        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

@@ -58,12 +58,17 @@ void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st);
 // h0 T [B*3000, d] -> A2 T [B*1500, 3*d], column = tap*d + channel (stride 2, pad 1)
 template <typename T>
 void im2col_conv2(const T* h0, T* out, int B, int d, cudaStream_t st);
+// Decode-step state lives on the device so that one captured CUDA graph can be replayed for every token:
+//   d_step[0] = pos (position of the token being fed), [1] = P (prompt length), [2] = stride of out_tokens,
+//   [3] = number of steps whose post-rules logits are tapped, [8 .. 8+P) = forced prompt tokens.
+constexpr int STEP_POS = 0, STEP_P = 1, STEP_STRIDE = 2, STEP_TAP = 3, STEP_PROMPT = 8, STEP_INTS = 32;
 // x[b] = E[tok[b]] + P[pos]   (f32 residual stream)
 template <typename T>
-void embed_tokens(const int32_t* tok, const T* E, const T* P, int pos, float* x, int B, int d, cudaStream_t st);
+void embed_tokens(const int32_t* tok, const T* E, const T* P, const int32_t* d_step, float* x, int B, int d, cudaStream_t st);
 // cache[b][pos][0:2d] = qkv[b][d:3d]
 template <typename T>
-void kv_append(const T* qkv, T* cache, int pos, int B, int d, int max_len, cudaStream_t st);
+void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st);
+void advance_step(int32_t* d_step, cudaStream_t st);
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 
 // ---- attention (attention.cu)
@@ -75,8 +80,9 @@ int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* o
 // decode attention (1 query per clip) over kv rows [Tk][2d] (K|V), clip stride kv_clip_stride elements.
 // q T [B, q_stride]; partial workspace f32 [decode_attention_partial_floats]; out T [B, d].
 template <typename T>
-void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, int B, int H, float* partial,
-                      T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+// d_tk (nullable): device int, the number of rows is *d_tk + 1 (self-attention cache at position pos) instead of Tk
+void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 size_t decode_attention_partial_floats(int B, int H);   // size of the partial workspace
 
 // ---- token selection (select.cu)
@@ -95,7 +101,8 @@ struct DecodeState {
     int32_t* n_unfinished;  // [1]
 };
 // one CTA per row: rules -> argmax -> finished/pad bookkeeping -> next input token
-void select_tokens(const float* logits, int V, int B, int gen_index, int out_stride, const RulesDev& rules, const DecodeState& st,
+// (inside the forced prompt it only feeds the next prompt token)
+void select_tokens(const float* logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
                    int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream);
 void decode_state_init(const DecodeState& st, int B, int first_tok, cudaStream_t stream);
 void set_cur_tok(const DecodeState& st, int B, int tok, cudaStream_t stream);

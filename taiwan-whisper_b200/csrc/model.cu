@@ -11,6 +11,7 @@
 
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -75,6 +76,17 @@ struct LayerW {
 
 }  // namespace
 
+struct GraphKey {
+    int B, eos, pad, ts_begin, no_ts, max_init;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(B, eos, pad, ts_begin, no_ts, max_init) < std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init);
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec;
+    uint64_t kernels;
+};
+
 struct tw_model {
     tw_ctx* ctx = nullptr;
     tw_model_desc desc{};
@@ -106,6 +118,11 @@ struct tw_model {
     int32_t* d_ids_tmp = nullptr;
     int32_t *d_out_tok = nullptr, *d_out_len = nullptr;
     int32_t* h_flag = nullptr;   // pinned
+    int32_t* h_step = nullptr;   // pinned staging of the step header
+    int32_t* d_step = nullptr;   // device step state (kernels.cuh STEP_*)
+    bool use_graph = true;       // replay one captured CUDA graph per decode step
+    cudaStream_t cap_stream = nullptr;
+    std::map<GraphKey, GraphEntry> graphs;
     // in-situ timing of the dominant kernel (cross-attention K/V streaming) for bench.py's roofline
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
@@ -301,6 +318,9 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, (void**)&m->d_out_len, B * sizeof(int32_t)));
     for (auto& ev : m->ev) TW_CUDA_OK(m->ctx, cudaEventCreate(&ev));
     TW_CUDA_OK(m->ctx, cudaMallocHost(&m->h_flag, 64));
+    TW_CUDA_OK(m->ctx, cudaMallocHost(&m->h_step, STEP_INTS * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_step, STEP_INTS * sizeof(int32_t)));
+    TW_CUDA_OK(m->ctx, cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
     return TW_OK;
 }
 
@@ -421,13 +441,74 @@ int upload_rules(tw_model* m, const tw_rules* R, RulesDev* out, cudaStream_t st)
     return TW_OK;
 }
 
+__global__ void fill_pad_kernel(int32_t* out_tokens, int B, int stride, int from_g, int pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int span = stride - from_g;
+    if (span > 0 && i < B * span) out_tokens[(int64_t)(i / span) * stride + from_g + (i % span)] = pad;
+}
+
+struct StepIo {
+    int32_t* out_tokens;
+    int32_t* out_lengths;
+    const int32_t* forced;
+    float* logits_tap;
+};
+
+// One decode step (all kernels of one token position).  Position, prompt and output stride are read from
+// m->d_step on the device, so the same launch sequence — or one captured CUDA graph — serves every position.
+template <typename T>
+int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, const StepIo& io, cudaStream_t st) {
+    const tw_model_desc& D = m->desc;
+    tw_ctx* ctx = m->ctx;
+    const int d = D.d_model, V = D.vocab, H = D.heads;
+    float* x = m->dx;
+    T* xn = (T*)m->dxn; T* qkv = (T*)m->dqkv; T* att = (T*)m->datt; T* q = (T*)m->dq; T* hmid = (T*)m->dhmid;
+    const size_t self_layer = (size_t)D.max_batch * D.max_target * 2 * d;
+    const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
+    const int32_t* d_pos = m->d_step + STEP_POS;
+    embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, m->d_step, x, B, d, st);
+    for (int l = 0; l < D.dec_layers; ++l) {
+        const LayerW& L = m->dec[l];
+        T* cache = (T*)m->self_kv + l * self_layer;
+        layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
+        kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st);
+        decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, 0, d_pos, B, H, m->dpartial, att, st);
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+        layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (m->prof_on && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
+            e0 = m->prof_ev[m->prof_used];
+            e1 = m->prof_ev[m->prof_used + 1];
+            m->prof_used += 2;
+        }
+        decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial,
+                            att, st, e0, e1);
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
+        layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+        TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+        ctx->launches += 8;       // 3 LN, append, 2 x (stream + combine); the GEMMs count themselves
+    }
+    layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
+    TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
+    select_tokens(m->dlogits, V, B, m->d_step, R, S, io.out_tokens, io.out_lengths, io.forced, io.logits_tap, st);
+    advance_step(m->d_step, st);
+    ctx->launches += 4;           // embed, LN, select, advance
+    return TW_OK;
+}
+
 template <typename T>
 int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev& R, int max_length, int32_t* out_tokens,
                 int32_t* out_lengths, const int32_t* forced, float* logits_tap, int tap_steps, cudaStream_t st) {
     const tw_model_desc& D = m->desc;
     tw_ctx* ctx = m->ctx;
-    const int d = D.d_model, V = D.vocab, H = D.heads;
     const int n_gen_max = max_length - P;
+    if (P > STEP_INTS - STEP_PROMPT) {
+        ctx->set_error(TW_E_INVALID, "decode: prompt longer than 24 tokens is not supported");
+        return TW_E_INVALID;
+    }
     DecodeState S;
     S.cur_tok = m->dstate;
     S.finished = m->dstate + D.max_batch;
@@ -438,62 +519,69 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     S.n_unfinished = m->dstate + 6 * D.max_batch;
     decode_state_init(S, B, prompt[0], st);
     TW_CUDA_OK(ctx, cudaMemsetAsync(out_lengths, 0, B * sizeof(int32_t), st));
-    float* x = m->dx;
-    T* xn = (T*)m->dxn; T* qkv = (T*)m->dqkv; T* att = (T*)m->datt; T* q = (T*)m->dq; T* hmid = (T*)m->dhmid;
-    const size_t self_layer = (size_t)D.max_batch * D.max_target * 2 * d;
-    const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
+    // step header -> device (pinned staging so the copy is stream-ordered)
+    int32_t* hs = m->h_step;
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(st));          // previous call may still be reading h_step
+    for (int i = 0; i < STEP_INTS; ++i) hs[i] = 0;
+    hs[STEP_POS] = 0; hs[STEP_P] = P; hs[STEP_STRIDE] = n_gen_max; hs[STEP_TAP] = logits_tap ? tap_steps : 0;
+    for (int i = 0; i < P; ++i) hs[STEP_PROMPT + i] = prompt[i];
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(m->d_step, hs, STEP_INTS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    ctx->launches += 1;
+
+    // CUDA graph of one step: production path only (no teacher forcing / taps / per-launch profiling events)
+    const bool want_graph = m->use_graph && !forced && !logits_tap && !m->prof_on;
+    // the graph bakes in its output pointers: decode into the model-owned buffers, copy out at the end
+    StepIo io{out_tokens, out_lengths, forced, logits_tap};
+    if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
+    if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
+    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts};
+    cudaGraphExec_t exec = nullptr;
+    uint64_t exec_kernels = 0;
+
     int32_t* h_unfinished = m->h_flag;
     *h_unfinished = B;
     bool check_pending = false;
-    // positions 0..P-1 consume the forced prompt (prefill as P single-token steps), then one step per token
+    int steps_done = 0;
     for (int pos = 0; pos < max_length - 1; ++pos) {
-        embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, pos, x, B, d, st);
-        for (int l = 0; l < D.dec_layers; ++l) {
-            const LayerW& L = m->dec[l];
-            T* cache = (T*)m->self_kv + l * self_layer;
-            layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
-            GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d);
-            const bool fused_append = sizeof(T) == 2 && m->use_tc && m->use_skinny && gemm_skinny_supported(B, 3 * d, d, qe);
-            if (fused_append) {                      // K|V columns land directly in the cache row of this position
-                qe.n_split = d;
-                qe.C2 = cache + (size_t)pos * 2 * d;
-                qe.ldc2 = (int64_t)D.max_target * 2 * d;
+        if (want_graph && pos >= 1 && !exec) {
+            auto it = m->graphs.find(key);
+            if (it != m->graphs.end()) {
+                exec = it->second.exec;
+                exec_kernels = it->second.kernels;
+            } else {
+                // capture one step on the model's private stream (nothing executes during capture)
+                cudaGraph_t graph = nullptr;
+                const uint64_t l0 = ctx->launches;
+                TW_CUDA_OK(ctx, cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+                int rc = launch_step<T>(m, B, R, S, io, m->cap_stream);
+                cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
+                if (rc != TW_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess || !graph) {
+                    ctx->set_error(TW_E_CUDA, std::string("decode graph capture failed: ") + cudaGetErrorString(ce));
+                    return TW_E_CUDA;
+                }
+                exec_kernels = ctx->launches - l0;
+                ctx->launches = l0;                       // nothing ran during capture
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) {
+                    ctx->set_error(TW_E_CUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+                    return TW_E_CUDA;
+                }
+                m->graphs[key] = GraphEntry{exec, exec_kernels};
             }
-            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
-            if (!fused_append) kv_append<T>(qkv, cache, pos, B, d, D.max_target, st);
-            decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, pos + 1, B, H, m->dpartial, att, st);
-            TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
-            layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
-            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (m->prof_on && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
-                e0 = m->prof_ev[m->prof_used];
-                e1 = m->prof_ev[m->prof_used + 1];
-                m->prof_used += 2;
-            }
-            decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, B, H, m->dpartial, att,
-                                st, e0, e1);
-            TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
-            layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
-            TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
-            TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
-            ctx->launches += 8;
         }
-        ctx->launches += 1;
-        if (pos < P - 1) {
-            set_cur_tok(S, B, prompt[pos + 1], st);      // still inside the forced prompt
-            ctx->launches += 1;
-            continue;
+        if (exec) {
+            TW_CUDA_OK(ctx, cudaGraphLaunch(exec, st));
+            ctx->launches += exec_kernels;
+        } else {
+            TW_CHECK(launch_step<T>(m, B, R, S, io, st));
         }
-        const int g = pos - (P - 1);                     // index of the token being generated
-        layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
-        TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
-        float* tap = (logits_tap && g < tap_steps) ? logits_tap + (size_t)g * B * V : nullptr;
-        select_tokens(m->dlogits, V, B, g, n_gen_max, R, S, out_tokens, out_lengths, forced, tap, st);
-        ctx->launches += 2;
+        ++steps_done;
+        const int g = pos - (P - 1);
         // early exit when every row has emitted EOS: the count is copied back every 8 tokens and read 8
         // tokens later, so the launch queue never drains (random-init models never emit EOS)
-        if ((g & 7) == 7) {
+        if (g >= 0 && (g & 7) == 7) {
             bool all_done = false;
             if (check_pending) {
                 TW_CUDA_OK(ctx, cudaEventSynchronize(m->ev[5]));
@@ -505,14 +593,17 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
                 check_pending = true;
             }
             if (all_done) {
-                // remaining positions: pad
-                for (int g2 = g + 1; g2 < n_gen_max; ++g2) {
-                    select_tokens(m->dlogits, V, B, g2, n_gen_max, R, S, out_tokens, out_lengths, forced, nullptr, st);
+                if (g + 1 < n_gen_max) {
+                    fill_pad_kernel<<<ceil_div(B * (n_gen_max - g - 1), 256), 256, 0, st>>>(io.out_tokens, B, n_gen_max, g + 1, R.pad);
                     ctx->launches += 1;
                 }
                 break;
             }
         }
+    }
+    if (want_graph && out_tokens != m->d_out_tok) {
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(out_tokens, m->d_out_tok, (size_t)B * n_gen_max * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(out_lengths, m->d_out_len, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     }
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
@@ -596,6 +687,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_tc = (D.dtype == TW_BF16) && !(g && strcmp(g, "simt") == 0);
     const char* ga = getenv("TWB200_ATTN");
     m->use_tc_attn = (D.dtype == TW_BF16) && !(ga && strcmp(ga, "simt") == 0);
+    const char* gg = getenv("TWB200_GRAPH");
+    m->use_graph = !(gg && strcmp(gg, "0") == 0);
     const char* gs = getenv("TWB200_SKINNY");
     // measured on B200 (profiles/r01_decode_kernels_ncu.md): the tcgen05 N=32-tile kernel beats the mma.sync skinny
     // kernel at every decode shape, so the skinny kernel is opt-in (TWB200_SKINNY=1) until it is reworked
@@ -617,6 +710,9 @@ void tw_model_free(tw_model* m) {
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_flag) cudaFreeHost(m->h_flag);
+    if (m->h_step) cudaFreeHost(m->h_step);
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+    if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     for (auto& ev : m->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : m->prof_ev) cudaEventDestroy(ev);
@@ -756,10 +852,11 @@ int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, cons
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TW_BF16)
-        decode_attention<__nv_bfloat16>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)kv, kv_clip_stride, Tk, B, H, scratch,
-                                        (__nv_bfloat16*)out, st);
+        decode_attention<__nv_bfloat16>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)kv, kv_clip_stride, Tk, nullptr, B, H,
+                                        scratch, (__nv_bfloat16*)out, st);
     else
-        decode_attention<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, B, H, scratch, (float*)out, st);
+        decode_attention<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, nullptr, B, H, scratch, (float*)out,
+                                st);
     ctx->launches += 2;
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;

@@ -60,7 +60,7 @@ __device__ __forceinline__ float masked_score(float raw, int i, const RulesDev& 
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_tokens_kernel(const float* __restrict__ logits, int V, int gen_index, int out_stride, RulesDev R, DecodeState S,
+select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __restrict__ d_step, RulesDev R, DecodeState S,
                      int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_lengths, const int32_t* __restrict__ forced,
                      float* __restrict__ logits_tap) {
     __shared__ Best s_text[32], s_ts[32];
@@ -68,6 +68,14 @@ select_tokens_kernel(const float* __restrict__ logits, int V, int gen_index, int
     __shared__ int s_tok;
     __shared__ int s_dom;
     const int b = blockIdx.x;
+    const int pos = d_step[STEP_POS], P = d_step[STEP_P], out_stride = d_step[STEP_STRIDE];
+    const int gen_index = pos - (P - 1);
+    if (gen_index < 0) {                       // still consuming the forced prompt: feed the next prompt token
+        if (threadIdx.x == 0) S.cur_tok[b] = d_step[STEP_PROMPT + pos + 1];
+        return;
+    }
+    if (gen_index >= out_stride) return;
+    if (logits_tap) logits_tap = (gen_index < d_step[STEP_TAP]) ? logits_tap + (int64_t)gen_index * gridDim.x * V : nullptr;
     const float* row = logits + (int64_t)b * V;
     const bool ts_mode = R.ts_begin >= 0;
     const int n_hist = S.n_gen[b];
@@ -155,10 +163,9 @@ select_tokens_kernel(const float* __restrict__ logits, int V, int gen_index, int
     }
 }
 
-void select_tokens(const float* logits, int V, int B, int gen_index, int out_stride, const RulesDev& rules, const DecodeState& st,
+void select_tokens(const float* logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
                    int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream) {
-    select_tokens_kernel<<<B, SEL_THREADS, 0, stream>>>(logits, V, gen_index, out_stride, rules, st, out_tokens, out_lengths, forced,
-                                                        logits_tap);
+    select_tokens_kernel<<<B, SEL_THREADS, 0, stream>>>(logits, V, d_step, rules, st, out_tokens, out_lengths, forced, logits_tap);
 }
 
 __global__ void decode_state_init_kernel(DecodeState S, int B, int first_tok) {
