@@ -31,6 +31,8 @@ struct GemmEpi {
     int n_split = 0x7fffffff;
     void* C2 = nullptr;
     int64_t ldc2 = 0;
+    const int32_t* d_row2 = nullptr;   // device int: extra row offset (*d_row2 * row2_stride elements) into C2 — the cache position
+    int64_t row2_stride = 0;
 };
 
 // CUDA-core FMA GEMM, fp32 accumulate in a fixed order; the fp32 check-mode path (T = float)

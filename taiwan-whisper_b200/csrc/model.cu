@@ -310,6 +310,7 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, &m->dhmid, B * D.ffn * e));
     TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * D.vocab * sizeof(float)));
     TW_CHECK(dev_alloc(m, (void**)&m->dpartial, decode_attention_partial_floats((int)B, D.heads) * sizeof(float)));
+    TW_CUDA_OK(m->ctx, cudaMemset(m->dpartial, 0, decode_attention_partial_floats((int)B, D.heads) * sizeof(float)));
     TW_CHECK(dev_alloc(m, (void**)&m->dstate, (6 * B + 4) * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
     TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
@@ -471,8 +472,17 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         const LayerW& L = m->dec[l];
         T* cache = (T*)m->self_kv + l * self_layer;
         layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
-        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
-        kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st);
+        GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d);
+        const bool fused_append = (sizeof(T) == 2) && m->use_tc && (d % 32 == 0);
+        if (fused_append) {      // the K|V columns of the fused QKV projection land in the cache row of this position
+            qe.n_split = d;
+            qe.C2 = cache;
+            qe.ldc2 = (int64_t)D.max_target * 2 * d;
+            qe.d_row2 = d_pos;
+            qe.row2_stride = 2 * d;
+        }
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
+        if (!fused_append) { kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st); ctx->launches += 1; }
         decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, 0, d_pos, B, H, m->dpartial, att, st);
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
@@ -489,7 +499,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
         TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
-        ctx->launches += 8;       // 3 LN, append, 2 x (stream + combine); the GEMMs count themselves
+        ctx->launches += 7;       // 3 LN, 2 x (attention stream + combine); the GEMMs (and an unfused append) count themselves
     }
     layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
     TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
@@ -674,7 +684,7 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
         return TW_E_INVALID;
     }
     if ((D.n_mel != 80 && D.n_mel != 128) || D.ffn <= 0 || D.ffn % 8 != 0 || D.enc_layers <= 0 || D.dec_layers <= 0 || D.vocab <= 0 ||
-        D.max_target <= 1 || D.max_batch <= 0 || (D.dtype != TW_BF16 && D.dtype != TW_F32)) {
+        D.max_target <= 1 || D.max_batch <= 0 || D.max_batch > 4096 || (D.dtype != TW_BF16 && D.dtype != TW_F32)) {
         ctx->set_error(TW_E_INVALID, "tw_model_load: bad model descriptor");
         return TW_E_INVALID;
     }
@@ -841,14 +851,20 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
 
 int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride, int Tk, int B,
                               int H, int dtype, void* out, void* stream) {
-    if (!ctx || !q || !kv || !out || B <= 0 || Tk <= 0 || H <= 0 || H > 20) return TW_E_INVALID;
+    if (!ctx || !q || !kv || !out || B <= 0 || B > 4096 || Tk <= 0 || H <= 0 || H > 20) return TW_E_INVALID;
+    // scratch sized (and zeroed: it holds the arrival counters) per call shape
     static float* scratch = nullptr;
     static size_t scratch_floats = 0;
+    static int scratch_B = -1, scratch_H = -1;
     const size_t need = decode_attention_partial_floats(B, H);
-    if (need > scratch_floats) {
-        if (scratch) cudaFree(scratch);
-        TW_CUDA_OK(ctx, cudaMalloc(&scratch, need * sizeof(float)));
-        scratch_floats = need;
+    if (need > scratch_floats || B != scratch_B || H != scratch_H) {
+        if (need > scratch_floats) {
+            if (scratch) cudaFree(scratch);
+            TW_CUDA_OK(ctx, cudaMalloc(&scratch, need * sizeof(float)));
+            scratch_floats = need;
+        }
+        TW_CUDA_OK(ctx, cudaMemset(scratch, 0, scratch_floats * sizeof(float)));
+        scratch_B = B; scratch_H = H;
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == TW_BF16)
