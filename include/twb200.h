@@ -166,6 +166,9 @@ TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float*
  *   encoder attention: qkv [B*S, 3*H*64] -> out [B*S, H*64]; impl 0 = CUDA-core kernel, 1 = tcgen05 flash kernel (bf16) */
 TW_API int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride,
                                      int Tk, int B, int H, int dtype, void* out, void* stream);
+/* same contract as tw_debug_decode_attention, through the single-launch short-cache self-attention kernel */
+TW_API int tw_debug_self_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride, int Tk,
+                                   int B, int H, int dtype, void* out, void* stream);
 TW_API int tw_debug_encoder_attention(tw_ctx* ctx, const void* qkv, void* out, int B, int S, int H, int dtype, int impl,
                                       void* stream);
 

@@ -412,6 +412,128 @@ decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_
     out[(int64_t)b * H * HD + h * HD + e] = from_f32<T>(o / l);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Self-attention over the short decoder cache (Tk = pos + 1 <= 448 rows): one CTA per (clip, group of 4 heads),
+// 8 warps striding over the rows with 4 rows of K|V in flight per warp, online softmax per head in registers,
+// warps merged through shared memory, normalised output written directly (single launch, no partial records).
+constexpr int SA_HG = 4;            // heads per CTA: 4 x 64 dims = 32 lanes x 8 elements
+constexpr int SA_WARPS = 8;
+constexpr int SA_UNR = 4;
+
+template <typename T> struct Ld8;
+template <> struct Ld8<float> {
+    struct Raw { float4 a, b; };
+    static __device__ __forceinline__ Raw load(const float* p) {
+        Raw r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+    }
+    static __device__ __forceinline__ void unpack(const Raw& r, float* f) {
+        f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+    }
+};
+template <> struct Ld8<__nv_bfloat16> {
+    typedef uint4 Raw;
+    static __device__ __forceinline__ Raw load(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+    static __device__ __forceinline__ void unpack(const Raw& raw, float* f) {
+        f[0] = __uint_as_float(raw.x << 16); f[1] = __uint_as_float(raw.x & 0xffff0000u);
+        f[2] = __uint_as_float(raw.y << 16); f[3] = __uint_as_float(raw.y & 0xffff0000u);
+        f[4] = __uint_as_float(raw.z << 16); f[5] = __uint_as_float(raw.z & 0xffff0000u);
+        f[6] = __uint_as_float(raw.w << 16); f[7] = __uint_as_float(raw.w & 0xffff0000u);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SA_WARPS * 32)
+self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
+                             const int32_t* __restrict__ d_tk, int H, T* __restrict__ out) {
+    __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
+    const int hg = blockIdx.x, b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d_tk) Tk = *d_tk + 1;
+    const int d = H * HD;
+    const int col = hg * SA_HG * HD + lane * 8;       // this lane's 8 dims inside the row
+    const bool active = col < d;
+    const T* kvb = kv + (int64_t)b * kv_clip_stride + (active ? col : 0);
+    float qf[8], of[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qf[e] = 0.0f; of[e] = 0.0f; }
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[e] = to_f32(q[(int64_t)b * q_stride + col + e]);
+    }
+    float mrun = -INFINITY, lrun = 0.0f;
+    for (int r0 = warp; r0 < Tk; r0 += SA_WARPS * SA_UNR) {
+        typename Ld8<T>::Raw kr[SA_UNR], vr[SA_UNR];
+#pragma unroll
+        for (int u = 0; u < SA_UNR; ++u) {
+            const int r = r0 + u * SA_WARPS;
+            if (r < Tk && active) {
+                kr[u] = Ld8<T>::load(kvb + (int64_t)r * 2 * d);
+                vr[u] = Ld8<T>::load(kvb + (int64_t)r * 2 * d + d);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SA_UNR; ++u) {
+            const int r = r0 + u * SA_WARPS;
+            if (r < Tk) {                                   // warp-uniform
+                float kf[8], vf[8];
+                if (active) { Ld8<T>::unpack(kr[u], kf); Ld8<T>::unpack(vr[u], vf); }
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+                }
+                float dot = 0.0f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dot = fmaf(qf[e], kf[e], dot);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                const float m_new = fmaxf(mrun, dot);
+                const float sc = __expf(mrun - m_new);
+                const float p = __expf(dot - m_new);
+                lrun = lrun * sc + p;
+                mrun = m_new;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) of[e] = fmaf(p, vf[e], of[e] * sc);
+            }
+        }
+    }
+    {
+        float* rec = s_rec[warp][lane >> 3];
+        if ((lane & 7) == 0) { rec[0] = mrun; rec[1] = lrun; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rec[2 + (lane & 7) * 8 + e] = of[e];
+    }
+    __syncthreads();
+    {
+        const int hh = threadIdx.x >> 6, e = threadIdx.x & 63;       // 256 threads = 4 heads x 64 dims
+        const int h = hg * SA_HG + hh;
+        if (h < H) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < SA_WARPS; ++w) m = fmaxf(m, s_rec[w][hh][0]);
+            float l = 0.0f, o = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SA_WARPS; ++w) {
+                const float sc = (s_rec[w][hh][0] == -INFINITY) ? 0.0f : __expf(s_rec[w][hh][0] - m);
+                l += s_rec[w][hh][1] * sc;
+                o += s_rec[w][hh][2 + e] * sc;
+            }
+            out[(int64_t)b * d + h * HD + e] = from_f32<T>(o / l);
+        }
+    }
+}
+
+template <typename T>
+void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
+                           T* out, cudaStream_t st) {
+    dim3 grid(ceil_div(H, SA_HG), B);
+    self_attention_decode_kernel<T><<<grid, SA_WARPS * 32, 0, st>>>(q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+}
+template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
+                                           cudaStream_t);
+template void self_attention_decode<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*,
+                                                   int, int, __nv_bfloat16*, cudaStream_t);
+
 static int g_da_sm_count = 0;
 size_t decode_attention_partial_floats(int B, int H) {
     if (g_da_sm_count == 0) {

@@ -483,7 +483,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         }
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
         if (!fused_append) { kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st); ctx->launches += 1; }
-        decode_attention<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, 0, d_pos, B, H, m->dpartial, att, st);
+        self_attention_decode<T>(qkv, 3 * d, cache, (int64_t)D.max_target * 2 * d, 0, d_pos, B, H, att, st);
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
@@ -499,7 +499,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
         TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
-        ctx->launches += 7;       // 3 LN, 2 x (attention stream + combine); the GEMMs (and an unfused append) count themselves
+        ctx->launches += 6;       // 3 LN, self-attention, cross-attention stream + combine; the GEMMs count themselves
     }
     layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
     TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
@@ -874,6 +874,20 @@ int tw_debug_decode_attention(tw_ctx* ctx, const void* q, int64_t q_stride, cons
         decode_attention<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, nullptr, B, H, scratch, (float*)out,
                                 st);
     ctx->launches += 2;
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_debug_self_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const void* kv, int64_t kv_clip_stride, int Tk, int B, int H,
+                            int dtype, void* out, void* stream) {
+    if (!ctx || !q || !kv || !out || B <= 0 || Tk <= 0 || H <= 0) return TW_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TW_BF16)
+        self_attention_decode<__nv_bfloat16>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)kv, kv_clip_stride, Tk, nullptr, B,
+                                             H, (__nv_bfloat16*)out, st);
+    else
+        self_attention_decode<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, nullptr, B, H, (float*)out, st);
+    ctx->launches += 1;
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

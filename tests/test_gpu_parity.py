@@ -176,7 +176,8 @@ def test_encoder_attention_kernels_vs_torch(B, S, H, impl):
 
 
 @pytest.mark.parametrize("Tk,B,H", [(1500, 3, 6), (1, 2, 2), (37, 5, 20), (448, 64, 2)])
-def test_decode_attention_kernel_vs_torch(Tk, B, H):
+@pytest.mark.parametrize("entry", ["tw_debug_decode_attention", "tw_debug_self_attention"])
+def test_decode_attention_kernel_vs_torch(Tk, B, H, entry):
     _cuda()
     from taiwan_whisper_b200 import lib as twlib
     ctx = twlib.Context.get(torch.cuda.current_device())
@@ -187,8 +188,8 @@ def test_decode_attention_kernel_vs_torch(Tk, B, H):
         kv = torch.randn((B, Tk + 3, 2 * d), device="cuda", generator=g).to(dt)
         q = (torch.randn((B, d), device="cuda", generator=g) * 0.3).to(dt)
         out = torch.zeros((B, d), device="cuda", dtype=dt)
-        ctx.check(ctx.lib.tw_debug_decode_attention(ctx.handle, q.data_ptr(), d, kv.data_ptr(), stride, Tk, B, H, tw_dt,
-                                                    out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        ctx.check(getattr(ctx.lib, entry)(ctx.handle, q.data_ptr(), d, kv.data_ptr(), stride, Tk, B, H, tw_dt,
+                                           out.data_ptr(), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         x = kv[:, :Tk].float().view(B, Tk, 2, H, 64)
         sc = torch.einsum("bhd,bthd->bht", q.float().view(B, H, 64), x[:, :, 0])
