@@ -243,7 +243,7 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count) {
 template <typename T>
 __global__ void __launch_bounds__(DA_THREADS, 1)
 decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
-                        const int32_t* __restrict__ d_tk, int B, int H, int stages, float* __restrict__ partial) {
+                        const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
     const int row_elems = 2 * d;
@@ -255,6 +255,10 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    // kv_static: the K|V store was written long before the previous kernel (cross-attention K/V of the window), so the
+    // producer may start streaming it while the previous kernel (the q projection) is still running
+    if (!(kv_static && warp == DA_WARPS)) pdl_wait();
     if (d_tk) Tk = *d_tk + 1;
     const int64_t total = (int64_t)B * Tk;
     const int R = da_rows_per_cta(total, gridDim.x);
@@ -293,6 +297,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                 }
                 r = seg_end;
             }
+            if (kv_static) pdl_wait();               // every thread of the grid observes the dependency before exiting
         }
         return;
     }
@@ -396,6 +401,8 @@ template <typename T>
 __global__ void __launch_bounds__(HD)
 decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_t* __restrict__ d_tk, int B, int grid, int H,
                          T* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
     if (d_tk) Tk = *d_tk + 1;
     const int R = da_rows_per_cta((int64_t)B * Tk, grid);
@@ -446,6 +453,8 @@ __global__ void __launch_bounds__(SA_WARPS * 32)
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
+    pdl_trigger();
+    pdl_wait();                                      // q and the newest cache row come from the QKV GEMM just before
     const int hg = blockIdx.x, b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (d_tk) Tk = *d_tk + 1;
@@ -527,7 +536,7 @@ template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                            T* out, cudaStream_t st) {
     dim3 grid(ceil_div(H, SA_HG), B);
-    self_attention_decode_kernel<T><<<grid, SA_WARPS * 32, 0, st>>>(q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+    launch_k(self_attention_decode_kernel<T>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
                                            cudaStream_t);
@@ -558,9 +567,11 @@ void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip
         attr_set[which] = true;
     }
     if (ev0) cudaEventRecord(ev0, st);
-    decode_attention_stream<T><<<p.G, DA_THREADS, p.smem, st>>>(q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H, p.stages, partial);
+    const int kv_static = d_tk ? 0 : 1;
+    launch_k(decode_attention_stream<T>, dim3(p.G), dim3(DA_THREADS), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
+             p.stages, kv_static, partial);
     if (ev1) cudaEventRecord(ev1, st);
-    decode_attention_combine<T><<<dim3(H, B), HD, 0, st>>>(partial, Tk, d_tk, B, p.G, H, out);
+    launch_k(decode_attention_combine<T>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
                                       cudaStream_t, cudaEvent_t, cudaEvent_t);

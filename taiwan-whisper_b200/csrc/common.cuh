@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 
 #include "../../include/twb200.h"
 
@@ -55,6 +56,30 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// ---- programmatic dependent launch (PDL) for the decode-step kernel chain.  Kernels launched through launch_k
+// while g_pdl is set may start before their predecessor has finished: each of them calls pdl_trigger() on entry
+// (lets its own successor be scheduled) and pdl_wait() before touching anything the predecessor produces, so
+// barrier/TMEM setup and weight prefetch overlap the predecessor's tail.  Without the launch attribute both
+// instructions are no-ops.
+extern thread_local bool g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

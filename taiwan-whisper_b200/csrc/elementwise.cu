@@ -9,6 +9,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  T* __restrict__ out, int M, int d) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -61,10 +63,62 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
     }
 }
 
+// Decode-step variant (M = batch rows): one CTA per row, one float4 per thread, two block reductions — the
+// warp-per-row kernel above would run 8 CTAs and is latency-bound at this size.
+template <typename T>
+__global__ void __launch_bounds__(320)
+layernorm_row_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     T* __restrict__ out, int d) {
+    __shared__ float s_part[2][10];
+    pdl_trigger();
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const bool act = 4 * tid < d;
+    // gamma / beta do not depend on the previous kernel: fetch them before the dependency wait
+    float4 g = make_float4(0, 0, 0, 0), bb = make_float4(0, 0, 0, 0);
+    if (act) {
+        g = *reinterpret_cast<const float4*>(gamma + 4 * tid);
+        bb = *reinterpret_cast<const float4*>(beta + 4 * tid);
+    }
+    pdl_wait();
+    float4 v = make_float4(0, 0, 0, 0);
+    if (act) v = *reinterpret_cast<const float4*>(x + (int64_t)row * d + 4 * tid);
+    float s = warp_sum((v.x + v.y) + (v.z + v.w));
+    if (lane == 0) s_part[0][warp] = s;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int w = 0; w < nwarp; ++w) tot += s_part[0][w];
+    const float mean = tot / (float)d;
+    const float a = act ? v.x - mean : 0.0f, b = act ? v.y - mean : 0.0f, c = act ? v.z - mean : 0.0f, e = act ? v.w - mean : 0.0f;
+    float q = warp_sum((a * a + b * b) + (c * c + e * e));
+    if (lane == 0) s_part[1][warp] = q;
+    __syncthreads();
+    float qt = 0.0f;
+    for (int w = 0; w < nwarp; ++w) qt += s_part[1][w];
+    const float rstd = rsqrtf(qt / (float)d + 1e-5f);
+    if (act) {
+        const float o0 = a * rstd * g.x + bb.x, o1 = b * rstd * g.y + bb.y, o2 = c * rstd * g.z + bb.z, o3 = e * rstd * g.w + bb.w;
+        T* orow = out + (int64_t)row * d;
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + 4 * tid) = make_float4(o0, o1, o2, o3);
+        } else {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(orow) + 4 * tid) = pk;
+        }
+    }
+}
+
 template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int M, int d, cudaStream_t st) {
     if (M <= 0) return;
-    layernorm_kernel<T><<<ceil_div(M, 8), 256, 0, st>>>(x, gamma, beta, out, M, d);
+    if (M <= 512 && d <= 1280) {
+        const int threads = ((d / 4 + 31) / 32) * 32;
+        launch_k(layernorm_row_kernel<T>, dim3(M), dim3(threads), 0, st, x, gamma, beta, out, d);
+        return;
+    }
+    launch_k(layernorm_kernel<T>, dim3(ceil_div(M, 8)), dim3(256), 0, st, x, gamma, beta, out, M, d);
 }
 template void layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
 template void layernorm<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, cudaStream_t);
@@ -147,6 +201,8 @@ template void im2col_conv2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, 
 template <typename T>
 __global__ void embed_kernel(const int32_t* __restrict__ tok, const T* __restrict__ E, const T* __restrict__ P,
                              const int32_t* __restrict__ d_step, float* __restrict__ x, int d) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const int t = tok[b];
     const int pos = d_step[0];
@@ -155,7 +211,7 @@ __global__ void embed_kernel(const int32_t* __restrict__ tok, const T* __restric
 }
 template <typename T>
 void embed_tokens(const int32_t* tok, const T* E, const T* P, const int32_t* d_step, float* x, int B, int d, cudaStream_t st) {
-    embed_kernel<T><<<B, 256, 0, st>>>(tok, E, P, d_step, x, d);
+    launch_k(embed_kernel<T>, dim3(B), dim3(256), 0, st, tok, E, P, d_step, x, d);
 }
 template void embed_tokens<float>(const int32_t*, const float*, const float*, const int32_t*, float*, int, int, cudaStream_t);
 template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, const int32_t*, float*, int, int,
@@ -165,6 +221,8 @@ template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, 
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ d_step, int d,
                                  int max_len) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const int pos = d_step[0];
     const T* src = qkv + (int64_t)b * 3 * d + d;
@@ -173,13 +231,17 @@ __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cach
 }
 template <typename T>
 void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st) {
-    kv_append_kernel<T><<<B, 256, 0, st>>>(qkv, cache, d_step, d, max_len);
+    launch_k(kv_append_kernel<T>, dim3(B), dim3(256), 0, st, qkv, cache, d_step, d, max_len);
 }
 template void kv_append<float>(const float*, float*, const int32_t*, int, int, int, cudaStream_t);
 template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const int32_t*, int, int, int, cudaStream_t);
 
-__global__ void advance_step_kernel(int32_t* d_step) { d_step[0] += 1; }
-void advance_step(int32_t* d_step, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(d_step); }
+__global__ void advance_step_kernel(int32_t* d_step) {
+    pdl_trigger();
+    pdl_wait();
+    d_step[0] += 1;
+}
+void advance_step(int32_t* d_step, cudaStream_t st) { launch_k(advance_step_kernel, dim3(1), dim3(1), 0, st, d_step); }
 
 __global__ void copy_f32_kernel(const float4* __restrict__ s, float4* __restrict__ d, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];

@@ -25,7 +25,7 @@ constexpr int TC_THREADS = 192;      // 6 warps
 constexpr int TC_EPI_WARP0 = 2;
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);     // BN 64 / 32: 8 stages of 24 / 20 KB
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -125,6 +125,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int k_blocks_total = (K + TC_BK - 1) / TC_BK;
     const int kb_per_split = (k_blocks_total + ksplit - 1) / ksplit;
 
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
@@ -151,6 +152,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // PDL prologue: the weight tiles of the first work item do not depend on the previous kernel — start
+            // streaming them (up to one ring of stages) before waiting for the producer of A
+            int prefetched = 0;
+            if ((int)blockIdx.x < num_tiles) {
+                const int ks = blockIdx.x % ksplit, mn = blockIdx.x / ksplit;
+                const int n_blk = mn % tiles_n;
+                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+                prefetched = min(Cfg::STAGES, kb1 - kb0);
+                for (int i = 0; i < prefetched; ++i) {
+                    const uint32_t fb = smem_u32(&full_bar[i]);
+                    mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                    tma_load_2d(&map_w, fb, smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, (kb0 + i) * TC_BK, n_blk * BN);
+                }
+            }
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -158,12 +174,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
                 const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-                    tma_load_2d(&map_a, fb, sa, kb * TC_BK, m_blk * TC_BM);
-                    tma_load_2d(&map_w, fb, sa + Cfg::A_BYTES, kb * TC_BK, n_blk * BN);
+                    if (prefetched > 0) {            // W already in flight for this stage: only A is missing
+                        --prefetched;
+                        tma_load_2d(&map_a, fb, sa, kb * TC_BK, m_blk * TC_BM);
+                    } else {
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                        tma_load_2d(&map_a, fb, sa, kb * TC_BK, m_blk * TC_BM);
+                        tma_load_2d(&map_w, fb, sa + Cfg::A_BYTES, kb * TC_BK, n_blk * BN);
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -202,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        pdl_wait();
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -335,6 +357,7 @@ int gemm_tc_init(tw_ctx* ctx) {
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES));
     return TW_OK;
 }
 
@@ -372,13 +395,14 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
         return TW_E_UNSUPPORTED;
     }
     // skinny (decode, M <= 128): the GEMM streams W once; narrow N tiles spread it over many SMs
-    const int BN = (M <= TC_BM) ? 32 : ((N > 128) ? 256 : 128);
+    // (N tiles of 32 unless that gives more tiles than SMs, then 64 so that one wave covers the matrix)
+    const int BN = (M <= TC_BM) ? ((ceil_div(N, 32) > g_sm_count) ? 64 : 32) : ((N > 128) ? 256 : 128);
     CUtensorMap ma, mw;
     TW_CHECK(get_map(ctx, A, M, K, lda, TC_BM, &ma));
     TW_CHECK(get_map(ctx, W, N, K, ldw, BN, &mw));
     int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
     int ksplit = 1;
-    if (BN == 32 && epi.mode == EPI_RESID) {
+    if (BN <= 64 && epi.mode == EPI_RESID) {
         // skinny residual GEMM: split K so that ~one wave of CTAs each streams a short K range
         const int kb = ceil_div(K, TC_BK);
         ksplit = g_sm_count / tiles;
@@ -389,11 +413,13 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     tiles *= ksplit;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
     if (BN == 256)
-        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<256>, dim3(grid), dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+    else if (BN == 64)
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<64>, dim3(grid), dim3(TC_THREADS), TcCfg<64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     else if (BN == 32)
-        gemm_tc_kernel<32><<<grid, TC_THREADS, TcCfg<32>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<32>, dim3(grid), dim3(TC_THREADS), TcCfg<32>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     else
-        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, st>>>(ma, mw, M, N, K, ksplit, epi);
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<128>, dim3(grid), dim3(TC_THREADS), TcCfg<128>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

@@ -18,6 +18,10 @@
 
 using namespace tw;
 
+namespace tw {
+thread_local bool g_pdl = false;
+}
+
 namespace {
 
 // ---- weight repack kernels -----------------------------------------------------------------
@@ -121,6 +125,7 @@ struct tw_model {
     int32_t* h_step = nullptr;   // pinned staging of the step header
     int32_t* d_step = nullptr;   // device step state (kernels.cuh STEP_*)
     bool use_graph = true;       // replay one captured CUDA graph per decode step
+    bool use_pdl = true;         // programmatic dependent launch inside the decode step
     cudaStream_t cap_stream = nullptr;
     std::map<GraphKey, GraphEntry> graphs;
     // in-situ timing of the dominant kernel (cross-attention K/V streaming) for bench.py's roofline
@@ -467,6 +472,11 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
     const size_t self_layer = (size_t)D.max_batch * D.max_target * 2 * d;
     const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
     const int32_t* d_pos = m->d_step + STEP_POS;
+    // PDL only on the bf16 product path: every kernel launched below goes through launch_k and executes pdl_wait()
+    struct PdlScope {
+        PdlScope(bool on) { g_pdl = on; }
+        ~PdlScope() { g_pdl = false; }
+    } pdl_scope(m->use_pdl && sizeof(T) == 2 && m->use_tc && !m->use_skinny);
     embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, m->d_step, x, B, d, st);
     for (int l = 0; l < D.dec_layers; ++l) {
         const LayerW& L = m->dec[l];
@@ -699,6 +709,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_tc_attn = (D.dtype == TW_BF16) && !(ga && strcmp(ga, "simt") == 0);
     const char* gg = getenv("TWB200_GRAPH");
     m->use_graph = !(gg && strcmp(gg, "0") == 0);
+    const char* gp = getenv("TWB200_PDL");
+    m->use_pdl = !(gp && strcmp(gp, "0") == 0);
     const char* gs = getenv("TWB200_SKINNY");
     // measured on B200 (profiles/r01_decode_kernels_ncu.md): the tcgen05 N=32-tile kernel beats the mma.sync skinny
     // kernel at every decode shape, so the skinny kernel is opt-in (TWB200_SKINNY=1) until it is reworked

@@ -40,10 +40,9 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
 }
 
 // masked score of token i for this row (everything except the "timestamps dominate" rule)
-__device__ __forceinline__ float masked_score(float raw, int i, const RulesDev& R, bool first, bool ts_mode, bool last_ts,
-                                              bool pen_ts, int ts_forbid_end) {
-    if (R.suppress_mask[i]) return -INFINITY;
-    if (first && R.begin_suppress_mask[i]) return -INFINITY;
+__device__ __forceinline__ float masked_score(float raw, bool suppressed, int i, const RulesDev& R, bool first, bool ts_mode,
+                                              bool last_ts, bool pen_ts, int ts_forbid_end) {
+    if (suppressed) return -INFINITY;
     if (ts_mode) {
         if (i == R.no_timestamps) return -INFINITY;
         if (last_ts) {
@@ -67,6 +66,8 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
     __shared__ float s_m[32], s_s[32];
     __shared__ int s_tok;
     __shared__ int s_dom;
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     const int pos = d_step[STEP_POS], P = d_step[STEP_P], out_stride = d_step[STEP_STRIDE];
     const int gen_index = pos - (P - 1);
@@ -92,13 +93,32 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
 
     Best bt = {-INFINITY, 0x7fffffff}, bs = {-INFINITY, 0x7fffffff};
     float lm = -INFINITY, ls = 0.0f;
-    for (int i = threadIdx.x; i < V; i += SEL_THREADS) {
-        const float v = masked_score(row[i], i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
-        if (i < split) {
-            bt = better(bt, Best{v, i});
-        } else {
-            bs = better(bs, Best{v, i});
-            if (v > -INFINITY) lse_merge(lm, ls, v, 1.0f);
+    // 8 independent loads in flight per thread (the logits were just written by the vocab GEMM: L2 latency-bound)
+    constexpr int U = 8;
+    for (int base = threadIdx.x; base < V; base += SEL_THREADS * U) {
+        float raw[U];
+        bool sup[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * SEL_THREADS;
+            raw[u] = -INFINITY;
+            sup[u] = true;
+            if (i < V) {
+                raw[u] = __ldg(row + i);
+                sup[u] = (__ldg(R.suppress_mask + i) != 0) || (first && __ldg(R.begin_suppress_mask + i) != 0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * SEL_THREADS;
+            if (i >= V) continue;
+            const float v = masked_score(raw[u], sup[u], i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
+            if (i < split) {
+                bt = better(bt, Best{v, i});
+            } else {
+                bs = better(bs, Best{v, i});
+                if (v > -INFINITY) lse_merge(lm, ls, v, 1.0f);
+            }
         }
     }
     bt = warp_best(bt);
@@ -156,7 +176,8 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
         const bool dom = s_dom != 0;
         float* tap = logits_tap + (int64_t)b * V;
         for (int i = threadIdx.x; i < V; i += SEL_THREADS) {
-            float v = masked_score(row[i], i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
+            const bool sup = (R.suppress_mask[i] != 0) || (first && R.begin_suppress_mask[i] != 0);
+            float v = masked_score(row[i], sup, i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
             if (dom && i < split) v = -INFINITY;
             tap[i] = v;
         }
@@ -165,7 +186,8 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
 
 void select_tokens(const float* logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
                    int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream) {
-    select_tokens_kernel<<<B, SEL_THREADS, 0, stream>>>(logits, V, d_step, rules, st, out_tokens, out_lengths, forced, logits_tap);
+    launch_k(select_tokens_kernel, dim3(B), dim3(SEL_THREADS), 0, stream, logits, V, d_step, rules, st, out_tokens, out_lengths, forced,
+             logits_tap);
 }
 
 __global__ void decode_state_init_kernel(DecodeState S, int B, int first_tok) {

@@ -1,0 +1,24 @@
+"""Short decode run at large-v3 width (d=1280, ffn=5120, 20 heads, vocab 51866, batch 64) with only 1 encoder and
+2 decoder layers, for an ncu launch list of the decode-step kernels (TWB200_GRAPH=0 so every launch is visible)."""
+import os
+import sys
+
+os.environ.setdefault("TWB200_GRAPH", "0")
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import hf_ref  # noqa: E402  (model object construction only)
+from taiwan_whisper_b200.configs import WhisperShape  # noqa: E402
+from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa: E402
+
+sh = WhisperShape("lv3-2dec", 128, 1280, 5120, 20, 1, 2, 51866)
+with torch.device("cuda"):
+    hf = hf_ref.build_hf_model(sh, seed=1)
+m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=64)
+enc = (torch.randn((64, 1500, 1280), device="cuda") * 0.5).bfloat16()
+prompt = m._init_tokens("zh", "transcribe", False)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+toks, lens = m.decode(enc, prompt, len(prompt) + n, False)
+torch.cuda.synchronize()
+print("ok", toks.shape)
