@@ -186,9 +186,9 @@ __device__ __forceinline__ void da_mbar_wait(uint32_t bar, uint32_t parity) {
         "DA_WAIT_DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void da_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void da_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
 template <typename T> struct Vec8;
@@ -278,6 +278,9 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     if (warp == DA_WARPS) {
         // ===================== producer =====================
         if (lane == 0) {
+            // the K|V store is streamed once per launch and is far larger than L2: mark the lines evict-first
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             int stage = 0;
             uint32_t phase = 0;
             int64_t r = row_begin;
@@ -292,7 +295,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                     const uint32_t fb = da_smem_u32(&full_bar[stage]);
                     da_mbar_expect_tx(fb, bytes);
                     da_bulk_g2s(da_smem_u32(reinterpret_cast<unsigned char*>(ring) + (size_t)stage * stage_bytes),
-                                src_clip + (r0 - (int64_t)b * Tk) * row_elems, bytes, fb);
+                                src_clip + (r0 - (int64_t)b * Tk) * row_elems, bytes, fb, policy);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 r = seg_end;

@@ -76,6 +76,11 @@ __device__ __forceinline__ void fa_tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void fa_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fa_ex2(float x) {           // single MUFU.EX2 (exp2f adds range fix-ups we do not need)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void fa_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fa_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -222,20 +227,26 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
             fa_fence_after();
             const int valid = S - j * FA_BK;            // keys >= valid are padding
             // pass 1: row max
+            const bool full_tile = valid >= FA_BK;      // only the last key tile of a clip is masked (warp-uniform)
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < FA_BK; c += 32) {
                 uint32_t v[32];
                 fa_tmem_ld32(tmem_S + lane_off + c, v);
                 fa_tmem_wait_ld();
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-                    mx = fmaxf(mx, s);
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float s = (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
+                        mx = fmaxf(mx, s);
+                    }
                 }
             }
             const float m_new = fmaxf(m_run, mx);
-            const float scale = exp2f((m_run - m_new) * LOG2E);     // 0 on the first tile (m_run = -inf)
+            const float scale = fa_ex2((m_run - m_new) * LOG2E);    // 0 on the first tile (m_run = -inf)
             const float mneg = -m_new * LOG2E;
             // the previous P V must have finished reading P before it is overwritten, and O_tile(j-1) is folded in
             if (j > 0) {
@@ -258,13 +269,24 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
                 fa_tmem_ld32(tmem_S + lane_off + c, v);
                 fa_tmem_wait_ld();
                 uint32_t pk[16];
+                if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = (c + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), LOG2E, mneg)) : 0.0f;
-                    const float p1 = (c + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)) : 0.0f;
-                    lsum += p0 + p1;
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg));
+                        const float p1 = fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg));
+                        lsum += p0 + p1;
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = (c + i < valid) ? fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg)) : 0.0f;
+                        const float p1 = (c + i + 1 < valid) ? fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)) : 0.0f;
+                        lsum += p0 + p1;
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
                 }
                 // 32 keys = 64 bytes = 4 chunks of 16 B; chunk index inside the 128-byte row: ((c % 64) / 8) + q
                 unsigned char* prow = sP + (c >> 6) * FA_TILE_BYTES + r * 128;

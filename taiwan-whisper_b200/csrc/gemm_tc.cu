@@ -264,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 if (epi.mode == EPI_STORE || epi.mode == EPI_GELU) {
                     if (epi.mode == EPI_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
                     }
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.C) + o;
                     if (n0 >= epi.n_split)       // column split (fused QKV: K|V go straight into the cache row of this position)
@@ -306,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         if (epi.mode == EPI_GELU_POS) {
                             const float* pp = epi.pos + (int64_t)(row % epi.pos_period) * N + n0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] = gelu_erf(v[j]) + __ldg(pp + j);
+                            for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] = gelu_erf_fast(v[j]) + __ldg(pp + j);
                         }
                         if (vec) {
 #pragma unroll
