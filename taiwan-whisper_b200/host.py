@@ -211,6 +211,33 @@ class B200WhisperFeatureExtractor:
 
 
 # --------------------------------------------------------------------------------------------
+def retrieve_segments(seq: np.ndarray, timestamp_begin: int, seek_num_frames: int, input_stride: int = 2):
+    """Host-side restatement of WhisperGenerationMixin._retrieve_segment (generation_whisper.py:1976-2073) for one
+    decoded window: split at consecutive timestamp tokens and compute by how many feature frames to advance.
+    Returns (list of token arrays, segment_offset)."""
+    seq = np.asarray(seq)
+    ts = seq >= timestamp_begin
+    single_timestamp_ending = len(seq) >= 2 and (not ts[-2]) and bool(ts[-1])
+    idx = np.where(ts[:-1] & ts[1:])[0] + 1 if len(seq) >= 2 else np.zeros(0, dtype=np.int64)
+    if len(idx) > 0:
+        slices = idx.tolist()
+        if single_timestamp_ending:
+            slices.append(len(seq))
+        else:
+            slices[-1] += 1          # keep the last timestamp token: "it was no single ending"
+        segments, last = [], 0
+        for cur in slices:
+            segments.append(seq[last:cur])
+            last = cur
+        if single_timestamp_ending:
+            offset = seek_num_frames
+        else:
+            offset = int(seq[last - 2] - timestamp_begin) * input_stride
+    else:
+        segments, offset = [seq], seek_num_frames
+    return segments, int(offset)
+
+
 _LANG_NAMES = {"chinese": "zh", "mandarin": "zh", "english": "en", "japanese": "ja", "cantonese": "yue", "korean": "ko",
                "german": "de", "french": "fr", "spanish": "es"}
 
@@ -424,11 +451,16 @@ class B200WhisperForConditionalGeneration:
     @torch.no_grad()
     def generate(self, input_features=None, *, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None,
                  num_beams: int = 1, return_timestamps: Optional[bool] = None, language: Optional[str] = None,
-                 task: Optional[str] = None, attention_mask=None, return_prompt: bool = False, **kwargs):
+                 task: Optional[str] = None, attention_mask=None, return_prompt: bool = False, seek_loop: bool = True,
+                 **kwargs):
         """ref: training/run_pseudo_labelling.py:864-876,917-918; prefiltering/validator_inference.py:41-47,78.
         Returns a LongTensor [B, L] of generated ids (after the forced prompt, as transformers >= 4.46 / 5.x
         return them; `return_prompt=True` prepends the prompt, the 4.45 layout ref :629,1009-1010 expects),
-        EOS stripped, right-padded with pad_token_id to the batch maximum.  One 30 s window per row."""
+        EOS stripped, right-padded with pad_token_id to the batch maximum.  One 30 s window per row.
+        With return_timestamps=True and seek_loop=True (default) the host runs the installed transformers' (5.x)
+        seek loop around the window primitive: split at consecutive timestamp tokens, advance to the last predicted
+        timestamp, re-encode the zero-padded remainder (generation_whisper.py:785-900, 1976-2073); seek_loop=False
+        decodes each window exactly once (the short-form behaviour of the 4.45 the reference pins)."""
         if num_beams not in (None, 1):
             raise NotImplementedError("twb200 implements greedy decoding only (num_beams=1), as the reference's "
                                       "pseudo-labelling launchers use")
@@ -453,6 +485,8 @@ class B200WhisperForConditionalGeneration:
         if max_length > self.shape.max_target:
             raise ValueError(f"max_length={max_length} exceeds max_target_positions={self.shape.max_target}")
         pad = self._rules(ts)["pad"]
+        if ts and seek_loop:
+            return self._generate_seek_loop(feats, prompt, max_length, pad, return_prompt)
         rows, lens_all = [], []
         for s in range(0, feats.shape[0], self.max_batch):
             chunk = feats[s:s + self.max_batch]
@@ -469,6 +503,41 @@ class B200WhisperForConditionalGeneration:
         if return_prompt:
             toks = torch.cat([torch.tensor(prompt, device=toks.device).expand(toks.shape[0], -1), toks], dim=1)
         return toks if feats.is_cuda else toks.cpu()
+
+    def _generate_seek_loop(self, feats, prompt, max_length, pad, return_prompt):
+        tsb = self.generation_config.no_timestamps_token_id + 1
+        B = feats.shape[0]
+        x = feats.to(self.device).float()
+        seek = [0] * B
+        segs = [[] for _ in range(B)]
+        while any(s < N_FRAMES for s in seek):
+            active = [i for i in range(B) if seek[i] < N_FRAMES]
+            nframes = [min(N_FRAMES - seek[i], N_FRAMES) for i in active]
+            chunk = torch.zeros((len(active), x.shape[1], N_FRAMES), dtype=torch.float32, device=self.device)
+            for j, i in enumerate(active):
+                chunk[j, :, :nframes[j]] = x[i, :, seek[i]:seek[i] + nframes[j]]
+            toks_l, lens_l = [], []
+            for s0 in range(0, len(active), self.max_batch):
+                enc = self.encode(chunk[s0:s0 + self.max_batch])
+                t, l = self.decode(enc, prompt, max_length, True)
+                toks_l.append(t)
+                lens_l.append(l)
+            toks = torch.cat(toks_l).cpu().numpy()
+            lens = torch.cat(lens_l).cpu().numpy()
+            for j, i in enumerate(active):
+                pieces, offset = retrieve_segments(toks[j, :lens[j]], tsb, nframes[j])
+                if offset <= 0:                 # HF would spin here (zero-length segment); always make progress
+                    offset = nframes[j]
+                segs[i].extend(pieces)
+                seek[i] += offset
+        rows = [np.concatenate(sg) if sg else np.zeros(0, np.int64) for sg in segs]
+        L = max((len(r) for r in rows), default=0)
+        out = torch.full((B, L), pad, dtype=torch.long)
+        for i, r in enumerate(rows):
+            out[i, :len(r)] = torch.from_numpy(r.astype(np.int64))
+        if return_prompt:
+            out = torch.cat([torch.tensor(prompt).expand(B, -1), out], dim=1)
+        return out.to(feats.device) if feats.is_cuda else out
 
     # forward() (training) is out of scope
 

@@ -129,3 +129,28 @@ def test_shapes_sheet():
     assert SHAPES["distil-large-v3"].dec_layers == 2     # ref: training/create_student_model.py:147-148
     for s in SHAPES.values():
         assert s.head_dim == 64
+
+
+def test_retrieve_segments_matches_hf():
+    """host seek-loop splitting == transformers' WhisperGenerationMixin._retrieve_segment on random windows."""
+    from transformers.models.whisper.generation_whisper import WhisperGenerationMixin
+
+    from taiwan_whisper_b200.host import retrieve_segments
+    tsb = 50365
+    rng = np.random.default_rng(5)
+    cases = [[tsb, 5, 6, tsb + 10, tsb + 10, 7, tsb + 60], [tsb, 5, 6, tsb + 10, tsb + 10, 7, 8], [5, 6, 7],
+             [tsb + 3], [tsb, tsb], [tsb, 9, tsb + 1500, tsb + 1500], [tsb, 9, tsb + 700, tsb + 700, tsb + 700, 3, tsb + 900]]
+    for _ in range(200):
+        n = int(rng.integers(1, 40))
+        seq = np.where(rng.random(n) < 0.35, tsb + rng.integers(0, 1500, n), rng.integers(0, 50000, n))
+        cases.append(seq.tolist())
+    for seq in cases:
+        for nframes in (3000, 1234):
+            t = torch.tensor(seq)
+            segs, off = WhisperGenerationMixin._retrieve_segment(
+                seek_sequence=t, seek_outputs=[t], time_offset=torch.zeros(1, dtype=torch.float64), timestamp_begin=tsb,
+                seek_num_frames=torch.tensor([nframes]), time_precision=0.02, time_precision_features=0.01, input_stride=2,
+                prev_idx=0, idx=0, return_token_timestamps=False, decoder_input_ids=torch.zeros((1, 3), dtype=torch.long))
+            mine, off2 = retrieve_segments(np.asarray(seq), tsb, nframes)
+            assert int(off) == off2, seq
+            assert [s["tokens"].tolist() for s in segs] == [m.tolist() for m in mine], seq

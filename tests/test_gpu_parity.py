@@ -250,7 +250,7 @@ def test_greedy_tokens_fp32_bit_identical(shape_name, timestamps):
     pcm, mel, ora = oracle_run(shape_name, 3, max_length, timestamps)
     m = b200_model(shape_name, "f32")
     ids = m.generate(torch.from_numpy(mel), max_length=max_length, num_beams=1, return_timestamps=timestamps,
-                     language="zh", task="transcribe").numpy()
+                     language="zh", task="transcribe", seek_loop=False).numpy()
     for b in range(3):
         ref = ora[b]["tokens"]
         assert ids[b, :len(ref)].tolist() == ref, (b, ids[b].tolist(), ref)
@@ -281,6 +281,31 @@ def test_tokens_vs_hf_golden(golden_dir):
                          task="transcribe").cpu().numpy()
         ref = g["tokens_nots"]
         assert ids.shape == ref.shape and np.array_equal(ids, ref)
+
+
+def test_timestamp_seek_loop_vs_hf_golden(golden_dir):
+    """return_timestamps=True: the host seek loop around the CUDA window primitive reproduces transformers 5.5's output
+    (several encoder/decoder passes per clip) token for token; seek_loop=False gives the single-window decode."""
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    from taiwan_whisper_b200.host import B200WhisperFeatureExtractor
+    for shape_name in ("tiny", "micro128"):
+        g = np.load(os.path.join(golden_dir, f"model_{shape_name}.npz"))
+        sh = SHAPES[shape_name]
+        fe = B200WhisperFeatureExtractor(feature_size=sh.n_mel)
+        feats = fe(list(dequantise(synth_batch(0, 2))), sampling_rate=16000, return_tensors="pt")["input_features"]
+        m = b200_model(shape_name, "f32")
+        max_length = int(g["max_length"])
+        ids = m.generate(feats, max_length=max_length, num_beams=1, return_timestamps=True, language="zh",
+                         task="transcribe").cpu().numpy()
+        ref = g["tokens_ts_seekloop"]
+        assert ids.shape == ref.shape and np.array_equal(ids, ref), (shape_name, ids.tolist(), ref.tolist())
+        single = m.generate(feats, max_length=max_length, num_beams=1, return_timestamps=True, language="zh",
+                            task="transcribe", seek_loop=False).cpu().numpy()
+        pcm, mel, ora = oracle_run(shape_name, 2, max_length, True)
+        for b in range(2):
+            t = ora[b]["tokens"]
+            assert single[b, :len(t)].tolist() == t
 
 
 @pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
