@@ -291,6 +291,8 @@ def main():
 
     if rank == 0:
         hbm, tf, which = peaks()
+        if not isinstance(stage, dict):
+            stage = {}
         bytes_per_launch = B * 1500 * 2 * sh.d_model * 2          # K|V rows of one decoder layer for the batch, bf16
         roof = None
         if prof_n > 0:
@@ -299,6 +301,28 @@ def main():
                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": which,
                     "traffic": None, "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
                     "algorithmic_bytes_per_launch": bytes_per_launch}
+        # per-stage roofline of the last e2e step (north_star: every stage against HBM or tensor-core peak)
+        d, ffn, L_e, L_d, V = sh.d_model, sh.ffn, sh.enc_layers, sh.dec_layers, sh.vocab
+        enc_flops = B * (2 * 3000 * d * sh.n_mel * 3 + 2 * 1500 * d * d * 3 +
+                         L_e * (8 * 1500 * d * d + 4 * 1500 * 1500 * d + 4 * 1500 * d * ffn))
+        xkv_flops = B * L_d * 4 * 1500 * d * d
+        w_dec = 2 * (L_d * (6 * d * d + 2 * d * ffn) + d * V)
+        steps_dec = args.max_length - 1
+        dec_bytes = steps_dec * (w_dec + B * L_d * 2 * 1500 * d * 2) + B * L_d * 2 * d * 2 * (steps_dec * (steps_dec + 1) // 2)
+        lm_bytes = B * (480000 * 2 + sh.n_mel * 3000 * 4)
+        stages = {}
+        if stage.get("encoder", 0) > 0:
+            stages = {
+                "logmel": {"bound": "hbm", "ms": stage["logmel"], "achieved_gbs": lm_bytes / stage["logmel"] / 1e6,
+                           "frac": lm_bytes / stage["logmel"] / 1e6 / hbm, "note": "includes the H2D copy of the int16 PCM"},
+                "encoder": {"bound": "tensor", "ms": stage["encoder"], "achieved_tflops": enc_flops / stage["encoder"] / 1e9,
+                            "frac": enc_flops / stage["encoder"] / 1e9 / tf},
+                "cross_kv": {"bound": "tensor", "ms": stage["cross_kv"], "achieved_tflops": xkv_flops / stage["cross_kv"] / 1e9,
+                             "frac": xkv_flops / stage["cross_kv"] / 1e9 / tf},
+                "decode": {"bound": "hbm", "ms": stage["decode"], "achieved_gbs": dec_bytes / stage["decode"] / 1e6,
+                           "frac": dec_bytes / stage["decode"] / 1e6 / hbm,
+                           "note": "weights + cross-K/V + self-K/V streamed once per token"},
+            }
         line = {
             "metric": "rtfx_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -310,7 +334,7 @@ def main():
                        "parallelism": f"manifest sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs larger than L2: each step streams >= 15 GB of K/V and weights (L2 is 126 MB)",
                        "stage_ms_last_step": stage},
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "stages": stages,
         }
         if hf_cpu is not None:
             line["cpu_baseline"] = cpu_baseline(args, hf_cpu)
