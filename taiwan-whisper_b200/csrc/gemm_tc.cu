@@ -30,7 +30,11 @@ template <int BN> struct TcCfg {
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered fp32 accumulator (power of two >= 32)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    // BN >= 128 (the M >> 128 GEMMs): the epilogue stages 128 x 128-byte boxes in two swizzled buffers and hands them to
+    // TMA (tensor store, or tensor reduce-add for the fp32 residual stream)
+    static constexpr bool TMA_EPI = (BN >= 128);
+    static constexpr int EPI_BYTES = TMA_EPI ? 2 * TC_BM * 128 : 0;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -88,6 +92,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+                 "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -104,13 +121,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K, int ksplit,
-               GemmEpi epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_c, int M, int N, int K, int ksplit, GemmEpi epi) {
     using Cfg = TcCfg<BN>;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    unsigned char* epi_smem = smem + Cfg::STAGES * Cfg::STAGE_BYTES;      // [2][128 rows][128 B] (TMA_EPI only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // [2]
@@ -129,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
+        if (Cfg::TMA_EPI) tma_prefetch_desc(&map_c);
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -226,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         pdl_wait();
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         int it = 0;
+        int epi_box = 0;                           // boxes handed to TMA so far (TMA_EPI)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int ks = tile % ksplit, mn = tile / ksplit;
             const int m_blk = mn / tiles_n, n_blk = mn % tiles_n;
@@ -234,6 +254,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tc_fence_after();
             const int row = m_blk * TC_BM + quarter * 32 + lane;
+            if constexpr (Cfg::TMA_EPI) {
+                // ---- TMA epilogue: registers -> swizzled smem box (128 rows x 128 B) -> tensor store / reduce-add.
+                // Row / column tails are clipped by the tensor map, so no guards are needed on the stores.
+                const bool out_bf16 = (epi.mode == EPI_STORE || epi.mode == EPI_GELU);
+                const int cols_per_box = out_bf16 ? 64 : 32;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+                const int r_in_tile = quarter * 32 + lane;
+                const bool issuer = (warp == TC_EPI_WARP0 && lane == 0);
+                for (int cb = 0; cb < BN; cb += cols_per_box) {
+                    const int nb0 = n_blk * BN + cb;
+                    if (nb0 >= N) break;                                   // uniform over the 4 warps
+                    unsigned char* buf = epi_smem + (epi_box & 1) * (TC_BM * 128);
+                    if (epi_box >= 2) {                                    // the store issued from this buffer two boxes ago
+                        if (issuer) tma_store_wait_read<1>();
+                        epi_bar_sync();
+                    }
+                    unsigned char* rowp = buf + r_in_tile * 128;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < cols_per_box; c0 += 32) {
+                        const int n0 = nb0 + c0;
+                        uint32_t r[32];
+                        tmem_ld32(t_row + cb + c0, r);
+                        tmem_ld_wait();
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (epi.bias && ks == 0) {
+                            if (n0 + 32 <= N) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n0 + j));
+                                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += __ldg(epi.bias + n0 + j);
+                            }
+                        }
+                        if (epi.mode == EPI_GELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+                        } else if (epi.mode == EPI_GELU_POS) {
+                            const float* pp = epi.pos + (int64_t)(row % epi.pos_period) * N + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]) + ((n0 + j < N) ? __ldg(pp + j) : 0.0f);
+                        }
+                        if (out_bf16) {             // 32 columns = 64 bytes = 16-byte chunks (c0/8) .. (c0/8)+3 of the 128-byte row
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * qd], v[8 * qd + 1]), h1 = __floats2bfloat162_rn(v[8 * qd + 2], v[8 * qd + 3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * qd + 4], v[8 * qd + 5]), h3 = __floats2bfloat162_rn(v[8 * qd + 6], v[8 * qd + 7]);
+                                uint4 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                const int chunk = (c0 >> 3) + qd;
+                                *reinterpret_cast<uint4*>(rowp + ((chunk ^ (r_in_tile & 7)) << 4)) = pk;
+                            }
+                        } else {                    // 32 fp32 columns = the whole 128-byte row
+#pragma unroll
+                            for (int qd = 0; qd < 8; ++qd)
+                                *reinterpret_cast<float4*>(rowp + ((qd ^ (r_in_tile & 7)) << 4)) =
+                                    make_float4(v[4 * qd], v[4 * qd + 1], v[4 * qd + 2], v[4 * qd + 3]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    epi_bar_sync();
+                    if (issuer) {
+                        if (epi.mode == EPI_RESID) tma_reduce_add_2d(&map_c, smem_u32(buf), nb0, m_blk * TC_BM);
+                        else tma_store_2d(&map_c, smem_u32(buf), nb0, m_blk * TC_BM);
+                        tma_store_commit();
+                    }
+                    ++epi_box;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+                continue;
+            }
             const bool row_ok = row < M;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
@@ -324,6 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
 
+    if (Cfg::TMA_EPI && warp == TC_EPI_WARP0 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -339,7 +438,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_sm_count = 148;
 
-using MapKey = std::tuple<const void*, int64_t, int64_t, int64_t, int>;
+using MapKey = std::tuple<const void*, int64_t, int64_t, int64_t, int, int>;
 static std::map<MapKey, CUtensorMap> g_maps;     // per process; a ctx is per device per process
 
 int gemm_tc_init(tw_ctx* ctx) {
@@ -361,8 +460,9 @@ int gemm_tc_init(tw_ctx* ctx) {
     return TW_OK;
 }
 
-static int get_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out) {
-    const MapKey key(ptr, rows, cols, ld, box_rows);
+// 2D row-major tensor map with 128-byte swizzle; esize 2 = bf16 (box 64 columns), 4 = f32 (box 32 columns)
+static int get_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, CUtensorMap* out, int esize = 2) {
+    const MapKey key(ptr, rows, cols, ld, box_rows, esize);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) {
         *out = it->second;
@@ -370,10 +470,11 @@ static int get_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int
     }
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+    const cuuint32_t box[2] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = g_encode(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void*>(ptr), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -397,9 +498,18 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     // skinny (decode, M <= 128): the GEMM streams W once; narrow N tiles spread it over many SMs
     // (N tiles of 32 unless that gives more tiles than SMs, then 64 so that one wave covers the matrix)
     const int BN = (M <= TC_BM) ? ((ceil_div(N, 32) > g_sm_count) ? 64 : 32) : ((N > 128) ? 256 : 128);
-    CUtensorMap ma, mw;
+    CUtensorMap ma, mw, mc;
     TW_CHECK(get_map(ctx, A, M, K, lda, TC_BM, &ma));
     TW_CHECK(get_map(ctx, W, N, K, ldw, BN, &mw));
+    mc = ma;
+    if (BN >= 128) {        // TMA epilogue: output map (bf16 for the store / GELU epilogues, f32 otherwise)
+        const int esize = (epi.mode == EPI_STORE || epi.mode == EPI_GELU) ? 2 : 4;
+        if ((epi.ldc * esize) % 16 || (reinterpret_cast<uintptr_t>(epi.C) & 15)) {
+            ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc: output must be 16-byte aligned with a 16-byte multiple row pitch");
+            return TW_E_UNSUPPORTED;
+        }
+        TW_CHECK(get_map(ctx, epi.C, M, N, epi.ldc, TC_BM, &mc, esize));
+    }
     int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
     int ksplit = 1;
     if (BN <= 64 && epi.mode == EPI_RESID) {
@@ -413,13 +523,13 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     tiles *= ksplit;
     const int grid = tiles < g_sm_count ? tiles : g_sm_count;
     if (BN == 256)
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<256>, dim3(grid), dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<256>, dim3(grid), dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, ma, mw, mc, M, N, K, ksplit, epi));
     else if (BN == 64)
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<64>, dim3(grid), dim3(TC_THREADS), TcCfg<64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<64>, dim3(grid), dim3(TC_THREADS), TcCfg<64>::SMEM_BYTES, st, ma, mw, mc, M, N, K, ksplit, epi));
     else if (BN == 32)
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<32>, dim3(grid), dim3(TC_THREADS), TcCfg<32>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<32>, dim3(grid), dim3(TC_THREADS), TcCfg<32>::SMEM_BYTES, st, ma, mw, mc, M, N, K, ksplit, epi));
     else
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<128>, dim3(grid), dim3(TC_THREADS), TcCfg<128>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<128>, dim3(grid), dim3(TC_THREADS), TcCfg<128>::SMEM_BYTES, st, ma, mw, mc, M, N, K, ksplit, epi));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }
