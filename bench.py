@@ -106,6 +106,27 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_decode_attention_stream_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, bench shape)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r01_decode_attention_stream_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        tot = []
+        for r in data:
+            b = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(name)
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+                b += float(r[i]) * scale
+            tot.append(b)
+        return sum(tot) / len(tot) if tot else None
+    except Exception:
+        return None
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (HF feature extractor + generate, fp32, all host
     threads) on a bounded sample of the workload: each step = 1 clip of the batch, full token budget."""
@@ -299,7 +320,9 @@ def main():
             ach = bytes_per_launch / (prof_ms / prof_n / 1000.0) / 1e9
             roof = {"kernel": "decode_attention_partial (cross-attention K/V streaming, 1 launch per layer per token)",
                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": which,
-                    "traffic": None, "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
+                    "traffic": ncu_traffic_bytes() if (args.model == MODEL and B == BATCH) else None,
+                    "traffic_source": "profiles/r01_decode_attention_stream.ncu-rep (ncu --set full, same shape)",
+                    "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
                     "algorithmic_bytes_per_launch": bytes_per_launch}
         # per-stage roofline of the last e2e step (north_star: every stage against HBM or tensor-core peak)
         d, ffn, L_e, L_d, V = sh.d_model, sh.ffn, sh.enc_layers, sh.dec_layers, sh.vocab
