@@ -115,36 +115,46 @@ struct LmSmem {
     float2 w400[LM_NBIN];
     float fbw[LM_MAX_NNZ];
     int fb_start[128], fb_count[128], fb_off[128];
+    unsigned short zpos[LM_NBIN];      // where bin k of the 200-point FFT lives inside a frame's z[] (digit-reversed order)
     float red[LM_THREADS / 32];
 };
 
 template <typename SampleT>
 __global__ void __launch_bounds__(LM_THREADS, 2)
-logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t* __restrict__ n_valid_arr,
+logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t* __restrict__ n_valid_arr, int B,
               int n_mel, const int* __restrict__ fb_start, const int* __restrict__ fb_count,
               const int* __restrict__ fb_off, const float* __restrict__ fb_w, int fb_nnz,
               float* __restrict__ out, float* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LmSmem& s = *reinterpret_cast<LmSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int f0 = blockIdx.x * LM_FR;
-    const SampleT* x = pcm + (int64_t)b * pcm_stride;
-    int64_t nv = n_valid_arr ? (int64_t)n_valid_arr[b] : (int64_t)TW_N_SAMPLES;
-    if (nv > pcm_stride) nv = pcm_stride;
-    if (nv > TW_N_SAMPLES) nv = TW_N_SAMPLES;
-    const int n_valid = (int)nv;
 
-    // ---- tables -> smem
+    // ---- tables -> smem, once per (persistent) CTA
     for (int i = tid; i < LM_NFFT; i += LM_THREADS) s.win[i] = g_tables.win[i];
     for (int i = tid; i < 200; i += LM_THREADS) s.w200[i] = g_tables.w200[i];
-    for (int i = tid; i < LM_NBIN; i += LM_THREADS) s.w400[i] = g_tables.w400[i];
+    for (int i = tid; i < LM_NBIN; i += LM_THREADS) {
+        s.w400[i] = g_tables.w400[i];
+        const int k = (i == 200) ? 0 : i, q = k >> 3;
+        s.zpos[i] = (unsigned short)(25 * (k & 7) + 5 * (q % 5) + q / 5);
+    }
     for (int i = tid; i < fb_nnz; i += LM_THREADS) s.fbw[i] = fb_w[i];
     for (int i = tid; i < n_mel; i += LM_THREADS) {
         s.fb_start[i] = fb_start[i];
         s.fb_count[i] = fb_count[i];
         s.fb_off[i] = fb_off[i];
     }
+
+    const int tiles_per_clip = (TW_N_FRAMES + LM_FR - 1) / LM_FR;
+    const int n_tiles = B * tiles_per_clip;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_clip;
+    const int f0 = (tile - b * tiles_per_clip) * LM_FR;
+    const SampleT* x = pcm + (int64_t)b * pcm_stride;
+    int64_t nv = n_valid_arr ? (int64_t)n_valid_arr[b] : (int64_t)TW_N_SAMPLES;
+    if (nv > pcm_stride) nv = pcm_stride;
+    if (nv > TW_N_SAMPLES) nv = TW_N_SAMPLES;
+    const int n_valid = (int)nv;
+    __syncthreads();            // previous tile fully consumed (and the tables are in place)
 
     // ---- stage samples: smem x[i] = xp[160 f0 + i], xp = reflect-padded (200) zero-extended clip
     const int base = LM_HOP * f0 - LM_NFFT / 2;    // clip index of x[0]; multiple of 8 samples
@@ -218,20 +228,19 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
     }
     __syncthreads();
 
-    // ---- real-FFT split + power: Z[k] lives at z[f][25 (k&7) + 5 ((k>>3)%5) + (k>>3)/5]
-    for (int t = tid; t < LM_FR * LM_NBIN; t += LM_THREADS) {
-        const int f = t / LM_NBIN, k = t - f * LM_NBIN;
-        const int ka = (k == 200) ? 0 : k;
-        const int kb = (k == 0 || k == 200) ? 0 : 200 - k;
-        const int qa = ka >> 3, qb = kb >> 3;
-        const float2 za = s.z[f][25 * (ka & 7) + 5 * (qa % 5) + qa / 5];
-        const float2 zb = s.z[f][25 * (kb & 7) + 5 * (qb % 5) + qb / 5];
+    // ---- real-FFT split + power, two bins per task: with E = (Z[k] + conj Z[200-k]) / 2, O = (Z[k] - conj Z[200-k]) / 2i
+    // and T = W400^k O:  |X[k]|^2 = |E + T|^2 and |X[200-k]|^2 = |E - T|^2
+    for (int t = tid; t < LM_FR * 101; t += LM_THREADS) {
+        const int f = t / 101, k = t - f * 101;
+        const float2 za = s.z[f][s.zpos[k]];
+        const float2 zb = s.z[f][s.zpos[200 - k]];
         const float er = 0.5f * (za.x + zb.x), ei = 0.5f * (za.y - zb.y);
         const float orr = 0.5f * (za.y + zb.y), oi = -0.5f * (za.x - zb.x);
         const float2 w = s.w400[k];
-        const float xr = er + (w.x * orr - w.y * oi);
-        const float xi = ei + (w.x * oi + w.y * orr);
-        s.pw[f][k] = xr * xr + xi * xi;
+        const float tr = w.x * orr - w.y * oi, ti = w.x * oi + w.y * orr;
+        const float ar = er + tr, ai = ei + ti, br = er - tr, bi = ei - ti;
+        s.pw[f][k] = ar * ar + ai * ai;
+        s.pw[f][200 - k] = br * br + bi * bi;        // k = 100 writes the same value twice
     }
     __syncthreads();
 
@@ -244,7 +253,7 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
         const int st = s.fb_start[m], cnt = s.fb_count[m], off = s.fb_off[m];
         float acc = 0.0f;
         for (int j = 0; j < cnt; ++j) acc = fmaf(s.fbw[off + j], s.pw[f][st + j], acc);
-        const float lv = log10f(fmaxf(acc, 1e-10f));
+        const float lv = __log10f(fmaxf(acc, 1e-10f));      // MUFU.LG2 path: |err| ~1e-7, the contract is 1e-4
         if (frame < TW_N_FRAMES) {
             out_b[(int64_t)m * TW_N_FRAMES + frame] = lv;
             lmax = fmaxf(lmax, lv);
@@ -259,6 +268,7 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
         for (int w = 1; w < LM_THREADS / 32; ++w) m = fmaxf(m, s.red[w]);
         atomic_max_float(&clip_max[b], m);
     }
+    }   // tile loop
 }
 
 __global__ void logmel_init_max(float* clip_max, int B) {
@@ -384,14 +394,15 @@ int logmel_run(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, 
     }
     const tw_ctx::MelBank& bank = ctx->banks[n_mel == 80 ? 0 : 1];
     logmel_init_max<<<ceil_div(B, 256), 256, 0, st>>>(ctx->d_clip_max, B);
-    dim3 grid(ceil_div(TW_N_FRAMES, LM_FR), B);
+    const int n_tiles = ceil_div(TW_N_FRAMES, LM_FR) * B;
+    const int grid = n_tiles < 2 * ctx->sm_count ? n_tiles : 2 * ctx->sm_count;      // persistent: 2 CTAs per SM
     if (pcm_dtype == TW_I16)
         logmel_kernel<int16_t><<<grid, LM_THREADS, sizeof(LmSmem), st>>>(
-            (const int16_t*)pcm, pcm_stride, n_valid, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
+            (const int16_t*)pcm, pcm_stride, n_valid, B, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
             bank.nnz, out, ctx->d_clip_max);
     else
         logmel_kernel<float><<<grid, LM_THREADS, sizeof(LmSmem), st>>>(
-            (const float*)pcm, pcm_stride, n_valid, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
+            (const float*)pcm, pcm_stride, n_valid, B, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
             bank.nnz, out, ctx->d_clip_max);
     const int per_clip4 = n_mel * TW_N_FRAMES / 4;
     dim3 g2(ceil_div(per_clip4, 256 * 4), B);
