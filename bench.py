@@ -203,8 +203,8 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from oracle import hf_ref            # only for building the HF model object + the cpu_baseline leg
     from taiwan_whisper_b200.configs import SHAPES
+    from taiwan_whisper_b200.hf_compat import build_hf_model
     from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration, log_mel
     from taiwan_whisper_b200.synth import synth_batch
 
@@ -218,7 +218,7 @@ def main():
 
     # random-init weights of the architecture (HF init), built directly on the GPU
     with torch.device(dev):
-        hf = hf_ref.build_hf_model(sh, seed=1234)
+        hf = build_hf_model(sh, seed=1234)
     model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev))
     hf_cpu = None
     if rank == 0 and not args.no_cpu_baseline:

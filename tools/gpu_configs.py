@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import hf_ref  # noqa: E402  (HF model object construction only)
+from taiwan_whisper_b200.hf_compat import build_hf_model  # noqa: E402
 from taiwan_whisper_b200.configs import SHAPES  # noqa: E402
 from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa: E402
 from taiwan_whisper_b200.synth import synth_batch  # noqa: E402
@@ -20,7 +20,7 @@ out = {}
 for name, B, max_length, ts in (("distil-large-v3", 128, 256, False), ("medium", 32, 448, True), ("tiny", 1, 64, False)):
     sh = SHAPES[name]
     with torch.device("cuda"):
-        hf = hf_ref.build_hf_model(sh, seed=1234)
+        hf = build_hf_model(sh, seed=1234)
     m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B)
     del hf
     pcm = torch.from_numpy(synth_batch(0, min(B, 16))).repeat((B + 15) // 16, 1)[:B].contiguous().pin_memory()

@@ -8,13 +8,13 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import hf_ref  # noqa: E402  (model object construction only)
+from taiwan_whisper_b200.hf_compat import build_hf_model  # noqa: E402
 from taiwan_whisper_b200.configs import WhisperShape  # noqa: E402
 from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa: E402
 
 sh = WhisperShape("lv3-2dec", 128, 1280, 5120, 20, 1, 2, 51866)
 with torch.device("cuda"):
-    hf = hf_ref.build_hf_model(sh, seed=1)
+    hf = build_hf_model(sh, seed=1)
 m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=64)
 enc = (torch.randn((64, 1500, 1280), device="cuda") * 0.5).bfloat16()
 prompt = m._init_tokens("zh", "transcribe", False)

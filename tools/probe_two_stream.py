@@ -9,13 +9,13 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import hf_ref  # noqa: E402  (HF model object construction only)
+from taiwan_whisper_b200.hf_compat import build_hf_model  # noqa: E402
 from taiwan_whisper_b200.configs import SHAPES  # noqa: E402
 from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa: E402
 
 sh = SHAPES["large-v3"]
 with torch.device("cuda"):
-    hf = hf_ref.build_hf_model(sh, seed=1234)
+    hf = build_hf_model(sh, seed=1234)
 ML = 256
 full = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=64)
 prompt = full._init_tokens("zh", "transcribe", False)
