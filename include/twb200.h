@@ -68,9 +68,10 @@ TW_API uint64_t tw_launch_count(const tw_ctx* ctx);
  * pipeline.py:40-58), called at ref training/run_pseudo_labelling.py:739 and
  * prefiltering/validator_inference.py:57-60, including the pad/trim to 480000 samples of
  * ref prefiltering/validator_inference.py:131-137.
- *   pcm        device, [B, pcm_stride] samples, int16 (dequantised x/32768) or float32
- *   n_valid    device int32 [B] or NULL: samples beyond n_valid[b] (and beyond pcm_stride) read as 0;
- *              values > 480000 are truncated
+ *   pcm        device, row b starts at pcm + b * pcm_stride samples; int16 (dequantised x/32768) or float32
+ *   n_valid    device int32 [B] or NULL: row b has n_valid[b] readable samples (NULL: pcm_stride); samples beyond
+ *              that read as 0 and anything beyond 480000 is truncated.  Rows may overlap (pcm_stride < n_valid):
+ *              windows of a long recording are taken without copying (taiwan-whisper_b200/longform.py)
  *   out        device float32 [B, n_mel, 3000]
  * n_mel must be 80 or 128. */
 TW_API int tw_logmel(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B,

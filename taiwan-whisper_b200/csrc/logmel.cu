@@ -150,9 +150,11 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
     const int b = tile / tiles_per_clip;
     const int f0 = (tile - b * tiles_per_clip) * LM_FR;
     const SampleT* x = pcm + (int64_t)b * pcm_stride;
-    int64_t nv = n_valid_arr ? (int64_t)n_valid_arr[b] : (int64_t)TW_N_SAMPLES;
-    if (nv > pcm_stride) nv = pcm_stride;
+    // n_valid is authoritative when given (rows may overlap: long-form windows are rows of pitch < 480000);
+    // without it a row is pcm_stride samples long
+    int64_t nv = n_valid_arr ? (int64_t)n_valid_arr[b] : pcm_stride;
     if (nv > TW_N_SAMPLES) nv = TW_N_SAMPLES;
+    if (nv < 0) nv = 0;
     const int n_valid = (int)nv;
     __syncthreads();            // previous tile fully consumed (and the tables are in place)
 

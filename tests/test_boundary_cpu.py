@@ -154,3 +154,29 @@ def test_retrieve_segments_matches_hf():
             mine, off2 = retrieve_segments(np.asarray(seq), tsb, nframes)
             assert int(off) == off2, seq
             assert [s["tokens"].tolist() for s in segs] == [m.tolist() for m in mine], seq
+
+
+def test_chunk_plan_matches_reference_chunker():
+    """window placement == ref training/flax/distil_whisper/pipeline.py:224-254 (restated inline here)."""
+    from taiwan_whisper_b200.longform import chunk_plan
+
+    def ref_plan(inputs_len, chunk_len, stride_left, stride_right):
+        step = chunk_len - stride_left - stride_right
+        starts = np.arange(0, inputs_len, step)
+        out = []
+        for st in starts:
+            en = st + chunk_len
+            sl = 0 if st == 0 else stride_left
+            last = (en > inputs_len) if stride_right > 0 else (en >= inputs_len)
+            out.append((min(en, inputs_len) - st, sl, 0 if last else stride_right))
+        return starts, out
+
+    for n in (1, 479_999, 480_000, 480_001, 1_000_000, 16000 * 600):
+        for (sl, sr) in ((80000, 80000), (0, 0), (16000, 32000)):
+            a, b = chunk_plan(n, 480000, sl, sr)
+            c, d = ref_plan(n, 480000, sl, sr)
+            assert np.array_equal(a, c) and b == d
+    starts, strides = chunk_plan(16000 * 600)           # 10 minutes, default stride chunk/6 each side
+    assert starts[1] - starts[0] == 320000 and strides[0][1] == 0 and strides[-1][2] == 0
+    with pytest.raises(ValueError):
+        chunk_plan(1000, 100, 60, 60)

@@ -71,6 +71,20 @@ def test_logmel_ragged_and_long():
         fe(rows[0], sampling_rate=8000)
 
 
+def test_chunked_longform_logmel():
+    """zero-copy windowing of a long recording (strided rows + n_valid) == log-mel of each padded window."""
+    _cuda()
+    from taiwan_whisper_b200.longform import chunk_plan, chunked_log_mel
+    rec = np.concatenate([synth_batch(20, 2).reshape(-1), synth_batch(22, 1)[0][:123_456]])     # 67.7 s
+    feats, strides = chunked_log_mel(torch.from_numpy(rec).cuda(), 80)
+    starts, ref_strides = chunk_plan(len(rec))
+    assert strides == ref_strides and feats.shape == (len(starts), 80, 3000)
+    x = dequantise(rec)
+    for i, st in enumerate(starts):
+        ref = logmel_np.log_mel(logmel_np.pad_or_trim(x[st:st + 480000]), 80)
+        assert np.abs(feats[i].cpu().numpy() - ref).max() < LOGMEL_TOL, i
+
+
 def test_logmel_empty_batch():
     _cuda()
     from taiwan_whisper_b200.host import log_mel
