@@ -29,7 +29,11 @@ template <int BN> struct TcCfg {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;                 // double-buffered fp32 accumulator (power of two >= 32)
+    // (probed, tools/probes/gemm_trace.py: at M = 64 the K loop runs at ~205 ns per K block whether 8 or 16 stages are in
+    // flight and whether 1 or 4 independent accumulators are used — it is paced by TMA delivery of the 96 x 128-byte rows
+    // per block, ~60 GB/s per SM, two thirds of which is the A tile every CTA re-reads from L2)
+    static constexpr int NACC = 1;
+    static constexpr int TMEM_COLS = 2 * BN * NACC;          // double-buffered fp32 accumulator (power of two >= 32)
     // BN >= 128 (the M >> 128 GEMMs): the epilogue stages 128 x 128-byte boxes in two swizzled buffers and hands them to
     // TMA (tensor store, or tensor reduce-add for the fp32 residual stream)
     static constexpr bool TMA_EPI = (BN >= 128);
@@ -119,6 +123,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#ifdef TW_GEMM_TRACE
+// probe build only (tools/probes/gemm_trace.py): per-CTA phase timestamps
+__device__ unsigned long long g_trace[256 * 8];
+__device__ __forceinline__ void trace(int slot) {
+    if (blockIdx.x < 256) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[blockIdx.x * 8 + slot] = t;
+    }
+}
+#define TW_TRACE(slot) trace(slot)
+#else
+#define TW_TRACE(slot)
+#endif
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -144,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int kb_per_split = (k_blocks_total + ksplit - 1) / ksplit;
 
     pdl_trigger();
+    if (threadIdx.x == 0) TW_TRACE(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_w);
@@ -167,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) TW_TRACE(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -220,24 +241,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * (BN * Cfg::NACC);
                 const int ks = tile % ksplit;
                 const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+                int kstep = 0;                          // K steps issued for this tile
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    if (it == 0 && kb == kb0) TW_TRACE(2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t a_desc = make_sw128_desc(sa);
                     const uint64_t b_desc = make_sw128_desc(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
+                    for (int k = 0; k < TC_BK / 16; ++k, ++kstep) {
                         // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        const int a_idx = kstep % Cfg::NACC;
+                        tc_mma_f16(d_tmem + a_idx * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kstep >= Cfg::NACC) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(smem_u32(&tmem_full[acc]));                      // accumulator ready
+                TW_TRACE(3);
             }
         }
     } else {
@@ -252,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+            if (warp == TC_EPI_WARP0 && lane == 0) TW_TRACE(4);
             tc_fence_after();
             const int row = m_blk * TC_BM + quarter * 32 + lane;
             if constexpr (Cfg::TMA_EPI) {
@@ -259,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 // Row / column tails are clipped by the tensor map, so no guards are needed on the stores.
                 const bool out_bf16 = (epi.mode == EPI_STORE || epi.mode == EPI_GELU);
                 const int cols_per_box = out_bf16 ? 64 : 32;
-                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+                const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (BN * Cfg::NACC);
                 const int r_in_tile = quarter * 32 + lane;
                 const bool issuer = (warp == TC_EPI_WARP0 && lane == 0);
                 for (int cb = 0; cb < BN; cb += cols_per_box) {
@@ -333,7 +359,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 continue;
             }
             const bool row_ok = row < M;
-            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (BN * Cfg::NACC);
+            // a short K range (split-K) may not have touched every accumulator
+            const int kb_n = min(k_blocks_total, ks * kb_per_split + kb_per_split) - ks * kb_per_split;
+            const int n_acc = min(Cfg::NACC, kb_n * (TC_BK / 16));
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int n0 = n_blk * BN + c0;
@@ -341,11 +370,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 uint32_t r[32];
                 tmem_ld32(t_row + c0, r);
                 tmem_ld_wait();
-                if (!row_ok) continue;
                 float v[32];
-                const bool full = (n0 + 32 <= N);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int a = 1; a < n_acc; ++a) {
+                    tmem_ld32(t_row + a * BN + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+                }
+                if (!row_ok) continue;
+                const bool full = (n0 + 32 <= N);
                 if (epi.bias && ks == 0) {
                     if (full) {
 #pragma unroll
@@ -422,6 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     }
 
+    if (warp == TC_EPI_WARP0 && lane == 0) TW_TRACE(5);
     if (Cfg::TMA_EPI && warp == TC_EPI_WARP0 && lane == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores
     tc_fence_before();
     __syncthreads();
@@ -429,7 +465,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
+    if (threadIdx.x == 0) TW_TRACE(6);
 }
+
+#ifdef TW_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) void tw_debug_trace_copy(void* dst_dev) {
+    void* p = nullptr;
+    cudaGetSymbolAddress(&p, g_trace);
+    cudaMemcpy(dst_dev, p, sizeof(unsigned long long) * 256 * 8, cudaMemcpyDeviceToDevice);
+    cudaMemset(p, 0, sizeof(unsigned long long) * 256 * 8);
+}
+#endif
 
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

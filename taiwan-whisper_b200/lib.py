@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtwb200.so")
+LIB_PATH = os.environ.get("TWB200_LIB", os.path.join(HERE, "libtwb200.so"))   # TWB200_LIB: probe builds (tools/probes)
 
 TW_OK, TW_E_INVALID, TW_E_CUDA, TW_E_NOMEM, TW_E_UNSUPPORTED, TW_E_SHAPE, TW_E_STATE = 0, -1, -2, -3, -4, -5, -6
 TW_F32, TW_BF16, TW_I16, TW_I32 = 0, 1, 2, 3
