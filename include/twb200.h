@@ -156,7 +156,7 @@ TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, d
 
 /* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
  * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,
- * 2: skinny weight-streaming kernel for M <= 64, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
+ * 2: mma.sync skinny kernel for M <= 64, 3: tcgen05 skinny kernel for M <= 64 with K % 64 == 0, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
  * (dtype), 2 C(f32) += , 3 C(f32) = GELU(.) + pos[row % pos_period], 4 C(f32) = . */
 TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
                   int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);

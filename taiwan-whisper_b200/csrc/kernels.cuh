@@ -46,7 +46,13 @@ int gemm_tc_init(tw_ctx* ctx);
 int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
             const GemmEpi& epi, cudaStream_t st);
 
-// skinny (M <= 64) weight-streaming GEMM for the decode steps (gemm_skinny.cu), bf16
+// tcgen05 GEMM specialised for M <= 64 (gemm_tc_skinny.cu): 4 K blocks per TMA box through 3-D tensor maps
+int gemm_tc_skinny_init(tw_ctx* ctx);
+bool gemm_tc_skinny_supported(int M, int N, int K, const GemmEpi& epi);
+int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
+                   const GemmEpi& epi, cudaStream_t st);
+
+// mma.sync weight-streaming GEMM for M <= 64 (gemm_skinny.cu), bf16; opt-in
 bool gemm_skinny_supported(int M, int N, int K, const GemmEpi& epi);
 int gemm_skinny(tw_ctx* ctx, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
                 const GemmEpi& epi, cudaStream_t st);

@@ -97,7 +97,8 @@ struct tw_model {
     int esz = 2;                 // bytes per element of the model dtype
     bool use_tc = false;         // tcgen05 GEMMs (bf16 only)
     bool use_tc_attn = false;    // tcgen05 encoder attention (bf16 only)
-    bool use_skinny = false;     // weight-streaming skinny GEMM for decode steps (bf16 only)
+    bool use_skinny = false;     // mma.sync skinny GEMM for decode steps (bf16 only, opt-in)
+    bool use_tc_skinny = true;   // tcgen05 skinny GEMM with multi-K-block TMA boxes for M <= 64
     std::vector<void*> allocs;
     size_t bytes = 0;
     // weights
@@ -346,6 +347,7 @@ int gemm<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* A, int64_t lda, const 
                         const GemmEpi& epi, cudaStream_t st) {
     m->ctx->launches += 1;
     if (m->use_tc && m->use_skinny && gemm_skinny_supported(M, N, K, epi)) return gemm_skinny(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
+    if (m->use_tc && m->use_tc_skinny && gemm_tc_skinny_supported(M, N, K, epi)) return gemm_tc_skinny(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     if (m->use_tc) return gemm_tc(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     gemm_simt<__nv_bfloat16>(A, lda, W, ldw, M, N, K, epi, st);
     return TW_OK;
@@ -666,6 +668,7 @@ int tw_ctx_create(int device, tw_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     TW_CHECK(logmel_init(ctx));
     TW_CHECK(gemm_tc_init(ctx));
+    TW_CHECK(gemm_tc_skinny_init(ctx));
     return TW_OK;
 }
 
@@ -709,6 +712,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_tc_attn = (D.dtype == TW_BF16) && !(ga && strcmp(ga, "simt") == 0);
     const char* gg = getenv("TWB200_GRAPH");
     m->use_graph = !(gg && strcmp(gg, "0") == 0);
+    const char* g3 = getenv("TWB200_TC_SKINNY");
+    m->use_tc_skinny = !(g3 && strcmp(g3, "0") == 0);
     const char* gp = getenv("TWB200_PDL");
     m->use_pdl = !(gp && strcmp(gp, "0") == 0);
     const char* gs = getenv("TWB200_SKINNY");
@@ -850,6 +855,7 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
     if (dtype == TW_F32) {
         gemm_simt<float>((const float*)A, K, (const float*)W, K, M, N, K, e, st);
     } else if (dtype == TW_BF16) {
+        if (use_tc == 3) return gemm_tc_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         if (use_tc == 2) return gemm_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         if (use_tc) return gemm_tc(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         gemm_simt<__nv_bfloat16>((const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);

@@ -128,11 +128,12 @@ def test_gemm_tcgen05_vs_torch(M, N, K, mode):
 @pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (3, 5120, 1280), (64, 1280, 5120), (1, 51866, 1280),
                                    (5, 384, 384), (64, 128, 128), (2, 384, 1536), (64, 51865, 384), (7, 1152, 384)])
 @pytest.mark.parametrize("mode", [0, 1, 2, 4])
-def test_gemm_skinny_vs_torch(M, N, K, mode):
+@pytest.mark.parametrize("impl", [2, 3])
+def test_gemm_skinny_vs_torch(M, N, K, mode, impl):
     _cuda()
     from tests.gpu_common import gemm_debug
-    if K > 1280 and mode != 2:
-        pytest.skip("K > 1280 is only used (and supported) with the residual epilogue")
+    if impl == 2 and K > 1280 and mode != 2:
+        pytest.skip("mma.sync skinny kernel: K > 1280 only with the residual epilogue")
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + mode)
     A = (torch.randn((M, K), device="cuda", generator=g) * 0.5).bfloat16()
     W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
@@ -140,7 +141,7 @@ def test_gemm_skinny_vs_torch(M, N, K, mode):
     C0 = torch.randn((M, N), device="cuda", generator=g)
     acc = A.float() @ W.float().T + bias
     ref = {0: acc, 1: torch.nn.functional.gelu(acc), 2: C0 + acc, 4: acc}[mode]
-    out = gemm_debug(A, W, bias, mode, 2, C_init=C0).float()
+    out = gemm_debug(A, W, bias, mode, impl, C_init=C0).float()
     tol = 2e-2 if mode in (0, 1) else 2e-3
     err = (out - ref).abs().max().item()
     assert err < tol * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
