@@ -337,7 +337,7 @@ def main():
         if stage.get("encoder", 0) > 0:
             stages = {
                 "logmel": {"bound": "hbm", "ms": stage["logmel"], "achieved_gbs": lm_bytes / stage["logmel"] / 1e6,
-                           "frac": lm_bytes / stage["logmel"] / 1e6 / hbm, "note": "includes the H2D copy of the int16 PCM"},
+                           "frac": lm_bytes / stage["logmel"] / 1e6 / hbm, "h2d_ms": stage.get("h2d")},
                 "encoder": {"bound": "tensor", "ms": stage["encoder"], "achieved_tflops": enc_flops / stage["encoder"] / 1e9,
                             "frac": enc_flops / stage["encoder"] / 1e9 / tf},
                 "cross_kv": {"bound": "tensor", "ms": stage["cross_kv"], "achieved_tflops": xkv_flops / stage["cross_kv"] / 1e9,

@@ -145,9 +145,9 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
                        const int32_t* prompt, int P, const tw_rules* rules, int max_length,
                        int32_t* out_tokens_host, int32_t* out_lengths_host, void* stream);
 
-/* Per-stage device time of the last tw_transcribe_host / tw_encode / tw_decode_greedy call in ms
- * (CUDA events on the call's stream): [0] log-mel, [1] encoder, [2] cross-K/V, [3] decode, [4] total. */
-TW_API int tw_last_stage_ms(tw_model* m, float out_ms[5]);
+/* Per-stage device time of the last tw_transcribe_host / tw_decode_greedy call in ms (CUDA events on the call's
+ * stream): [0] log-mel, [1] encoder, [2] cross-K/V, [3] decode (incl. the D2H of the ids), [4] total, [5] H2D copy. */
+TW_API int tw_last_stage_ms(tw_model* m, float out_ms[6]);
 
 /* In-situ CUDA-event timing of the path's dominant kernel (the decode cross-attention K/V streaming
  * kernel, one sampled launch per decode step at the middle decoder layer).  Reads and resets the

@@ -133,9 +133,8 @@ struct tw_model {
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
     int prof_used = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float stage_ms[5] = {0, 0, 0, 0, 0};
-    bool ev_valid[6] = {false, false, false, false, false, false};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6]: before the H2D copy
+    bool ev_valid[7] = {false, false, false, false, false, false, false};
 };
 
 namespace {
@@ -800,7 +799,7 @@ int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* pro
             : decode_impl<float>(m, B, prompt, P, R, max_length, out_tokens, out_lengths, forced, logits_tap, tap_steps, st);
     cudaEventRecord(m->ev[4], st);
     m->ev_valid[2] = m->ev_valid[3] = m->ev_valid[4] = true;
-    m->ev_valid[0] = m->ev_valid[1] = false;
+    m->ev_valid[0] = m->ev_valid[1] = m->ev_valid[6] = false;
     return r;
 }
 
@@ -818,13 +817,14 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
     const int n_gen = max_length - P;
     RulesDev R;
     TW_CHECK(upload_rules(m, rules, &R, st));
-    cudaEventRecord(m->ev[0], st);
+    cudaEventRecord(m->ev[6], st);
     TW_CUDA_OK(ctx, cudaMemcpyAsync(m->ws_pcm, pcm_host, (size_t)B * TW_N_SAMPLES * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     const int32_t* nv = nullptr;
     if (n_valid_host) {
         TW_CUDA_OK(ctx, cudaMemcpyAsync(m->ws_nvalid, n_valid_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         nv = m->ws_nvalid;
     }
+    cudaEventRecord(m->ev[0], st);
     TW_CHECK(logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st));
     cudaEventRecord(m->ev[1], st);
     int r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st)
@@ -843,6 +843,7 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
     cudaEventRecord(m->ev[4], st);
     TW_CUDA_OK(ctx, cudaStreamSynchronize(st));
     for (int i = 0; i < 5; ++i) m->ev_valid[i] = true;
+    m->ev_valid[6] = true;
     return TW_OK;
 }
 
@@ -957,17 +958,18 @@ int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* 
     return TW_OK;
 }
 
-int tw_last_stage_ms(tw_model* m, float out_ms[5]) {
+int tw_last_stage_ms(tw_model* m, float out_ms[6]) {
     if (!m || !out_ms) return TW_E_INVALID;
-    for (int i = 0; i < 5; ++i) out_ms[i] = 0.0f;
+    for (int i = 0; i < 6; ++i) out_ms[i] = 0.0f;
     for (int i = 0; i < 4; ++i)
         if (m->ev_valid[i] && m->ev_valid[i + 1]) {
             if (cudaEventSynchronize(m->ev[i + 1]) == cudaSuccess) cudaEventElapsedTime(&out_ms[i], m->ev[i], m->ev[i + 1]);
         }
-    int first = -1;
-    for (int i = 0; i < 5; ++i)
-        if (m->ev_valid[i]) { first = i; break; }
-    if (first >= 0 && first < 4 && m->ev_valid[4]) cudaEventElapsedTime(&out_ms[4], m->ev[first], m->ev[4]);
+    if (m->ev_valid[6] && m->ev_valid[0]) cudaEventElapsedTime(&out_ms[5], m->ev[6], m->ev[0]);
+    int first = m->ev_valid[6] ? 6 : -1;
+    for (int i = 0; i < 5 && first < 0; ++i)
+        if (m->ev_valid[i]) first = i;
+    if (first >= 0 && first != 4 && m->ev_valid[4]) cudaEventElapsedTime(&out_ms[4], m->ev[first], m->ev[4]);
     return TW_OK;
 }
 

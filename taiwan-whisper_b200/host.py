@@ -443,9 +443,9 @@ class B200WhisperForConditionalGeneration:
         return float(ms.value), int(n.value)
 
     def last_stage_ms(self):
-        buf = (C.c_float * 5)()
+        buf = (C.c_float * 6)()
         self.ctx.lib.tw_last_stage_ms(self.handle, buf)
-        return dict(zip(("logmel", "encoder", "cross_kv", "decode", "total"), [float(x) for x in buf]))
+        return dict(zip(("logmel", "encoder", "cross_kv", "decode", "total", "h2d"), [float(x) for x in buf]))
 
     # ---- the reference's call
     @torch.no_grad()
