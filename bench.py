@@ -275,13 +275,14 @@ def main():
     stage = model.last_stage_ms()
     # roofline pass: the same K steps again with a CUDA-event pair around one cross-attention launch per decode
     # step (per-launch events cannot ride in the replayed CUDA graph, so this pass launches the kernels directly)
-    prof_ms, prof_n = 0.0, 0
+    prof_ms, prof_n, prof_bytes = 0.0, 0, 0.0
     if rank == 0:
         model.profile(True)
         for i in range(min(K, 2)):
             step_device(W + i)
         torch.cuda.synchronize()
         prof_ms, prof_n = model.profile(False)
+        prof_bytes = getattr(model, "last_profile_bytes", 0.0)
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -315,6 +316,8 @@ def main():
         if not isinstance(stage, dict):
             stage = {}
         bytes_per_launch = B * 1500 * 2 * sh.d_model * 2          # K|V rows of one decoder layer for the batch, bf16
+        if prof_bytes > 0:                                        # split decode: one launch streams one sub-batch
+            bytes_per_launch = int(prof_bytes)
         roof = None
         if prof_n > 0:
             ach = bytes_per_launch / (prof_ms / prof_n / 1000.0) / 1e9

@@ -154,9 +154,15 @@ TW_API int tw_last_stage_ms(tw_model* m, float out_ms[6]);
  * accumulated samples (either pointer may be NULL), then enables/disables sampling for later calls. */
 TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch);
 
+/* Test / profiling switch (calling thread): the tw_debug_* attention entry points use the small-footprint kernel
+ * variants of the split decode (3-stage K|V stream, 64-register self-attention). */
+TW_API void tw_debug_set_lite(int on);
+/* Test / profiling switch (calling thread): tw_debug_* launches carry the programmatic-dependent-launch attribute. */
+TW_API void tw_debug_set_pdl(int on);
+
 /* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
  * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,
- * 2: mma.sync skinny kernel for M <= 64, 3: tcgen05 skinny kernel for M <= 64 with K % 64 == 0, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
+ * 2: mma.sync skinny kernel for M <= 64, 3: tcgen05 skinny kernel for M <= 64 with K % 64 == 0, 4: its small-footprint variant for M <= 32 used by the split decode, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
  * (dtype), 2 C(f32) += , 3 C(f32) = GELU(.) + pos[row % pos_period], 4 C(f32) = . */
 TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
                   int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);

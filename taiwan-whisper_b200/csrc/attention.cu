@@ -7,6 +7,8 @@
 //    head in registers, partials merged by a second tiny kernel (flash-decoding split over time).
 // Arithmetic: HF WhisperAttention.forward (modeling_whisper.py:284-358): q already scaled by
 // head_dim^-0.5 (folded into the weights), softmax in fp32, no mask in the encoder.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace tw {
@@ -157,8 +159,10 @@ template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_b
 // of 8-row stages (8 x 2d elements, contiguous in HBM) into a shared-memory ring (mbarrier
 // complete_tx), 8 consumer warps take one row each per stage: per-head dot products with the query
 // held in registers, online softmax, P.V accumulation, all in fp32.  At the end of a clip segment the
-// warps merge through shared memory and emit one partial record (m, l, o[64]) per head; a small
-// second kernel merges the records of a clip.  Record index = cta + clip (unique, <= G + B - 2).
+// warps merge through shared memory (tree merge, 4-record buffer) and emit one partial record (m, l, o[64])
+// per head; a small second kernel merges the records of a clip.  Record index = cta + clip (unique, <= G + B - 2).
+// Variants measured on B200 and rejected (profiles/r01_split_decode.md): 8 warps with the refill issued by the last
+// warp to release a stage (shared-memory counter), and warp-private rings of single-row copies — both 10-15 % slower.
 constexpr int DA_WARPS = 8;        // consumer warps == rows per stage
 constexpr int DA_MAXSLOT = 5;      // ceil(H*8/32) with H <= 20
 constexpr int DA_PSTRIDE = HD + 2; // partial record: m, l, o[64]
@@ -223,7 +227,7 @@ struct DaPlan {
     int stages;
     size_t smem;
 };
-static DaPlan da_plan(int total_rows, int H, int esz, int sm_count) {
+static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stages) {
     DaPlan p;
     int g = ceil_div(total_rows, DA_WARPS);
     if (g > sm_count) g = sm_count;
@@ -231,9 +235,10 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count) {
     p.G = g;
     p.R = ceil_div(total_rows, g);
     const size_t stage_bytes = (size_t)DA_WARPS * 2 * H * HD * esz;
-    const size_t merge_bytes = (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float);
+    const size_t merge_bytes = (size_t)(DA_WARPS / 2) * H * DA_PSTRIDE * sizeof(float);
     int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
     if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
+    if (st > max_stages) st = max_stages;
     if (st < 2) st = 2;
     p.stages = st;
     p.smem = st * stage_bytes + merge_bytes + 256;
@@ -250,7 +255,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     const uint32_t stage_bytes = (uint32_t)DA_WARPS * row_elems * sizeof(T);
     T* ring = reinterpret_cast<T*>(da_raw);
     float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)DA_WARPS * H * DA_PSTRIDE * sizeof(float));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(DA_WARPS / 2) * H * DA_PSTRIDE * sizeof(float));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
@@ -364,38 +369,59 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
             if (lane == 0) da_mbar_arrive(da_smem_u32(&empty_bar[stage]));
             if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        // ---- merge the 8 warps of this clip segment -> one partial record per head
+        // ---- merge the 8 warps of this clip segment -> one partial record per head.  Tree merge through a
+        // 4-record buffer (warps 4-7 -> 0-3, 2-3 -> 0-1, 1 -> 0): half the shared memory of an 8-record buffer,
+        // which is what lets a decode-step GEMM CTA of the other sub-batch share the SM (model.cu, split decode).
 #pragma unroll
-        for (int s = 0; s < DA_MAXSLOT; ++s) {
-            const int slot = lane + 32 * s;
-            if (slot < nslots) {
-                const int h = slot >> 3, e0 = (slot & 7) * 8;
-                float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
-                if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
+        for (int half = DA_WARPS / 2; half >= 1; half >>= 1) {
+            if (warp >= half && warp < 2 * half) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
+                for (int s = 0; s < DA_MAXSLOT; ++s) {
+                    const int slot = lane + 32 * s;
+                    if (slot < nslots) {
+                        const int h = slot >> 3, e0 = (slot & 7) * 8;
+                        float* rec = merge + ((size_t)(warp - half) * H + h) * DA_PSTRIDE;
+                        if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
+            if (warp < half) {
+#pragma unroll
+                for (int s = 0; s < DA_MAXSLOT; ++s) {
+                    const int slot = lane + 32 * s;
+                    if (slot < nslots) {
+                        const int h = slot >> 3, e0 = (slot & 7) * 8;
+                        const float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
+                        const float m2 = rec[0], l2 = rec[1];
+                        const float m_new = fmaxf(mrun[s], m2);
+                        const float sc1 = (mrun[s] == -INFINITY) ? 0.0f : __expf(mrun[s] - m_new);
+                        const float sc2 = (m2 == -INFINITY) ? 0.0f : __expf(m2 - m_new);
+                        lrun[s] = lrun[s] * sc1 + l2 * sc2;
+                        mrun[s] = m_new;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) of[s][e] = of[s][e] * sc1 + rec[2 + e0 + e] * sc2;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
+        }
+        if (warp == 0) {
+            float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
+#pragma unroll
+            for (int s = 0; s < DA_MAXSLOT; ++s) {
+                const int slot = lane + 32 * s;
+                if (slot < nslots) {
+                    const int h = slot >> 3, e0 = (slot & 7) * 8;
+                    float* prec = prec_base + (size_t)h * DA_PSTRIDE;
+                    if ((slot & 7) == 0) { prec[0] = mrun[s]; prec[1] = lrun[s]; }
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float2*>(prec + 2 + e0 + e) = make_float2(of[s][e], of[s][e + 1]);
+                }
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
-        float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
-        for (int i = threadIdx.x; i < H * HD; i += DA_WARPS * 32) {
-            const int h = i / HD, e = i % HD;
-            float m = -INFINITY;
-#pragma unroll
-            for (int w = 0; w < DA_WARPS; ++w) m = fmaxf(m, merge[((size_t)w * H + h) * DA_PSTRIDE]);
-            float l = 0.0f, o = 0.0f;
-#pragma unroll
-            for (int w = 0; w < DA_WARPS; ++w) {
-                const float* rec = merge + ((size_t)w * H + h) * DA_PSTRIDE;
-                const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
-                l += rec[1] * sc;
-                o += rec[2 + e] * sc;
-            }
-            float* prec = prec_base + (size_t)h * DA_PSTRIDE;
-            if (e == 0) { prec[0] = m; prec[1] = l; }
-            prec[2 + e] = o;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
         r = seg_end;
     }
 }
@@ -428,7 +454,6 @@ decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_
 // warps merged through shared memory, normalised output written directly (single launch, no partial records).
 constexpr int SA_HG = 4;            // heads per CTA: 4 x 64 dims = 32 lanes x 8 elements
 constexpr int SA_WARPS = 8;
-constexpr int SA_UNR = 4;
 
 template <typename T> struct Ld8;
 template <> struct Ld8<float> {
@@ -451,8 +476,10 @@ template <> struct Ld8<__nv_bfloat16> {
     }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(SA_WARPS * 32)
+// SA_UNR = rows in flight per warp.  The <T, 2> variant is capped at 64 registers so that a CTA fits next to a resident
+// cross-attention streaming CTA of the other sub-batch (split decode, model.cu).
+template <typename T, int SA_UNR>
+__global__ void __launch_bounds__(SA_WARPS * 32, SA_UNR == 2 ? 4 : 1)
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
@@ -539,7 +566,10 @@ template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                            T* out, cudaStream_t st) {
     dim3 grid(ceil_div(H, SA_HG), B);
-    launch_k(self_attention_decode_kernel<T>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+    if (g_decode_lite && sizeof(T) == 2)
+        launch_k(self_attention_decode_kernel<T, 2>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+    else
+        launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
                                            cudaStream_t);
@@ -559,26 +589,36 @@ size_t decode_attention_partial_floats(int B, int H) {
 
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, bool stream_pdl) {
     (void)decode_attention_partial_floats(B, H);
-    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count);
+    // split decode: 3 stages (144 KB with the merge buffer) leave room for a decode-step GEMM CTA on the same SM
+    static const int env_stages = getenv("TWB200_DA_STAGES") ? atoi(getenv("TWB200_DA_STAGES")) : 0;      // tuning knob
+    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, g_decode_lite ? 3 : (env_stages >= 2 ? env_stages : DA_MAX_STAGES));
     if (d_tk) p.G = g_da_sm_count;               // row count only known on the device: launch every CTA
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
         cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        // keep the SM's shared-memory carveout at its maximum so that CTAs of other decode-step kernels fit next to this one
+        if (!(getenv("TWB200_CARVEOUT") && atoi(getenv("TWB200_CARVEOUT")) == 0))
+            cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set[which] = true;
     }
     if (ev0) cudaEventRecord(ev0, st);
     const int kv_static = d_tk ? 0 : 1;
+    // stream_pdl = false (split decode): as a programmatic dependent the CTAs would become resident — 144 KB of shared
+    // memory each — while their predecessor still runs, and keep the other sub-batch's streaming CTAs off the SMs
+    const bool pdl_saved = g_pdl;
+    if (!stream_pdl) g_pdl = false;
     launch_k(decode_attention_stream<T>, dim3(p.G), dim3(DA_THREADS), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
              p.stages, kv_static, partial);
+    g_pdl = pdl_saved;
     if (ev1) cudaEventRecord(ev1, st);
     launch_k(decode_attention_combine<T>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
-                                      cudaStream_t, cudaEvent_t, cudaEvent_t);
+                                      cudaStream_t, cudaEvent_t, cudaEvent_t, bool);
 template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*, int, int,
-                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
+                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t, bool);
 
 }  // namespace tw

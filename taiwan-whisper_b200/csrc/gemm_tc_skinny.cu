@@ -11,6 +11,8 @@
 // Same roles as gemm_tc.cu: warp 0 TMA producer (weights prefetched before griddepcontrol.wait), warp 1 MMA
 // issuer + TMEM owner, warps 2-5 epilogue (bias / GELU / fp32 residual add with split-K atomics / fp32 store /
 // KV-cache scatter of the fused QKV projection).
+#include <stdlib.h>
+
 #include <map>
 #include <tuple>
 
@@ -20,16 +22,22 @@ namespace tw {
 
 constexpr int SK2_THREADS = 192;
 constexpr int SK2_KSUB = 4;                   // K blocks (of 64) per TMA box / pipeline stage
-constexpr int SK2_A_SUB = 64 * 64 * 2;        // 64-row A tile of one K block
 
-template <int BN> struct Sk2Cfg {
+// AROWS = rows of the A box (64, or 32 for the "lite" variant used by the split decode: 2 stages x 32 KB and <= 80
+// registers per thread, so that one CTA fits next to a resident cross-attention streaming CTA of the other sub-batch).
+template <int BN, int AROWS> struct Sk2Cfg {
+    static constexpr bool LITE = (AROWS == 32);
+    static constexpr int A_SUB = AROWS * 64 * 2;                           // A tile of one K block
     static constexpr int W_SUB = BN * 64 * 2;
-    static constexpr int A_REGION = SK2_KSUB * SK2_A_SUB;
-    static constexpr int STAGE_BYTES = SK2_KSUB * (SK2_A_SUB + W_SUB);     // 48 KB (BN 32) / 64 KB (BN 64)
-    static constexpr int STAGES = (BN == 32) ? 4 : 3;
+    static constexpr int A_REGION = SK2_KSUB * A_SUB;
+    static constexpr int STAGE_BYTES = SK2_KSUB * (A_SUB + W_SUB);         // 48 KB (BN 32) / 64 KB (BN 64) / 32 KB (lite)
+    static constexpr int STAGES = LITE ? 2 : ((BN == 32) ? 4 : 3);
+    static constexpr int MIN_CTAS = LITE ? 4 : 1;                          // register cap: 65536 / (192 * 4) -> 80
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-    static_assert(SK2_KSUB * W_SUB >= SK2_A_SUB, "the M=128 read of the last A tile must stay inside the stage");
+    // the MMA runs as M = 128 and reads 128 x 128 B from the start of every A tile: the read of the last tile must stay
+    // inside the stage (rows >= AROWS are never stored)
+    static_assert((SK2_KSUB - 1) * A_SUB + 128 * 128 <= STAGE_BYTES, "the M=128 read of the last A tile must stay inside the stage");
 };
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -38,11 +46,11 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(SK2_THREADS, 1)
+template <int BN, int AROWS>
+__global__ void __launch_bounds__(SK2_THREADS, Sk2Cfg<BN, AROWS>::MIN_CTAS)
 gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
                       int ksplit, GemmEpi epi) {
-    using Cfg = Sk2Cfg<BN>;
+    using Cfg = Sk2Cfg<BN, AROWS>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -141,7 +149,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const int nsub = min(SK2_KSUB, kb1 - kb);      // K blocks of this stage that belong to the split
                     for (int j = 0; j < nsub; ++j) {
-                        const uint64_t a_desc = make_sw128_desc(sa + j * SK2_A_SUB);
+                        const uint64_t a_desc = make_sw128_desc(sa + j * Cfg::A_SUB);
                         const uint64_t b_desc = make_sw128_desc(sa + Cfg::A_REGION + j * Cfg::W_SUB);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
@@ -309,8 +317,11 @@ int gemm_tc_skinny_init(tw_ctx* ctx) {
         }
         g_sk2_encode = reinterpret_cast<Sk2EncodeFn>(fn);
     }
-    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32>::SMEM_BYTES));
-    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<64>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32, 64>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<64, 64>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32, 32>::SMEM_BYTES));
+    if (!(getenv("TWB200_CARVEOUT") && atoi(getenv("TWB200_CARVEOUT")) == 0))
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // probe once whether the driver accepts the 3-D view (K-block stride 128 B < row stride)
     static __nv_bfloat16* probe = nullptr;
     if (!probe) {
@@ -332,9 +343,11 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
         ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc_skinny: unsupported shape / alignment");
         return TW_E_UNSUPPORTED;
     }
-    const int BN = (ceil_div(N, 32) > ctx->sm_count) ? 64 : 32;
+    // lite: set by the split decode (model.cu) — small enough to share an SM with a streaming cross-attention CTA
+    const bool lite = g_decode_lite && M <= 32;
+    const int BN = (!lite && ceil_div(N, 32) > ctx->sm_count) ? 64 : 32;
     CUtensorMap ma, mw;
-    TW_CHECK(sk2_map(ctx, A, M, K, lda, 64, &ma));
+    TW_CHECK(sk2_map(ctx, A, M, K, lda, lite ? 32 : 64, &ma));
     TW_CHECK(sk2_map(ctx, W, N, K, ldw, BN, &mw));
     int tiles = ceil_div(N, BN);
     int ksplit = 1;
@@ -350,10 +363,12 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     // the kernel splits K in units of K blocks: make kb_per_split a multiple of KSUB by construction
     // (k_blocks_total / ksplit rounded up to whole stages)
-    if (BN == 32)
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+    if (lite)
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32, 32>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32, 32>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+    else if (BN == 32)
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     else
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<64, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<64, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

@@ -90,7 +90,8 @@ int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* o
 template <typename T>
 // d_tk (nullable): device int, the number of rows is *d_tk + 1 (self-attention cache at position pos) instead of Tk
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                      bool stream_pdl = true);
 size_t decode_attention_partial_floats(int B, int H);
 // single-launch self-attention over the short decoder cache (Tk = *d_tk + 1 when d_tk is given)
 template <typename T>

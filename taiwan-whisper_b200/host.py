@@ -437,9 +437,11 @@ class B200WhisperForConditionalGeneration:
 
     def profile(self, enable: bool):
         """Reads + resets the in-situ samples of the dominant kernel, then (de)activates sampling.
-        Returns (total_ms, launches)."""
-        ms, n = C.c_float(0), C.c_int(0)
-        self.ctx.check(self.ctx.lib.tw_profile(self.handle, 1 if enable else 0, C.byref(ms), C.byref(n), None))
+        Returns (total_ms, launches); `last_profile_bytes` holds the K|V bytes of one sampled launch (one sub-batch
+        of the batch when the decode step is split)."""
+        ms, n, nb = C.c_float(0), C.c_int(0), C.c_double(0)
+        self.ctx.check(self.ctx.lib.tw_profile(self.handle, 1 if enable else 0, C.byref(ms), C.byref(n), C.byref(nb)))
+        self.last_profile_bytes = float(nb.value)
         return float(ms.value), int(n.value)
 
     def last_stage_ms(self):
