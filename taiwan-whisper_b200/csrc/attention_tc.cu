@@ -16,6 +16,7 @@
 // Keys beyond the clip length (the 1536-padded tail, which TMA fills with the next clip's rows or zeros)
 // are masked to -inf before the softmax.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -93,6 +94,11 @@ __host__ __device__ constexpr uint32_t fa_idesc(int M, int N, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// VAR 1 (default): the TMEM load of the next 32 score columns is issued before the math of the current ones (+6 % on B200);
+// VAR 0 (TWB200_FA_VARIANT=0): one load at a time.  Measured and dropped (profiles/r01_encoder_attention_ncu.md): a lazy
+// running max (single pass over the scores), a share of the exponentials as an FMA-pipe polynomial, back-off in the
+// producer / MMA-issuer waits — none of them faster.
+template <int VAR>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int S, int H) {
     extern __shared__ unsigned char fa_raw[];
@@ -222,32 +228,101 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
 #pragma unroll
         for (int i = 0; i < FA_D; ++i) o_acc[i] = 0.0f;
         float m_run = -INFINITY, l_run = 0.0f, scale_prev = 1.0f;
-        for (int j = 0; j < n_tiles; ++j) {
-            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
-            fa_fence_after();
-            const int valid = S - j * FA_BK;            // keys >= valid are padding
-            // pass 1: row max
-            const bool full_tile = valid >= FA_BK;      // only the last key tile of a clip is masked (warp-uniform)
+        // ---- the two passes over the 128 score columns of this row (TMEM lane), 32 columns at a time
+        // pass A: raw row max (masked columns excluded)
+        auto max_pass = [&](int valid, bool full_tile) -> float {
             float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < FA_BK; c += 32) {
-                uint32_t v[32];
-                fa_tmem_ld32(tmem_S + lane_off + c, v);
-                fa_tmem_wait_ld();
+            auto fold = [&](const uint32_t* v, int c) {
                 if (full_tile) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-                        mx = fmaxf(mx, s);
-                    }
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+                }
+            };
+            if (VAR & 1) {
+                uint32_t va[32], vb[32];
+                fa_tmem_ld32(tmem_S + lane_off, va);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); fold(va, 0);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); fold(vb, 32);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); fold(va, 64);
+                fa_tmem_wait_ld(); fold(vb, 96);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < FA_BK; c += 32) {
+                    uint32_t v[32];
+                    fa_tmem_ld32(tmem_S + lane_off + c, v);
+                    fa_tmem_wait_ld();
+                    fold(v, c);
                 }
             }
-            const float m_new = fmaxf(m_run, mx);
+            return mx;
+        };
+        // pass B: P = exp2(s*log2e - m*log2e) -> bf16 -> shared memory (K-major, 128-byte swizzle); returns the row sum
+        auto exp_pass = [&](float mneg, int valid, bool full_tile) -> float {
+            float lsum0 = 0.0f, lsum1 = 0.0f;
+            auto chunk = [&](const uint32_t* v, int c) {
+                uint32_t pk[16];
+                if (full_tile) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                        const float p0 = fa_ex2(fmaf(s0, LOG2E, mneg));
+                        const float p1 = fa_ex2(fmaf(s1, LOG2E, mneg));
+                        lsum0 += p0;
+                        lsum1 += p1;
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const bool ok0 = c + i < valid, ok1 = c + i + 1 < valid;
+                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+                        const float p0 = ok0 ? fa_ex2(fmaf(s0, LOG2E, mneg)) : 0.0f;
+                        const float p1 = ok1 ? fa_ex2(fmaf(s1, LOG2E, mneg)) : 0.0f;
+                        lsum0 += p0;
+                        lsum1 += p1;
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
+                }
+                // 32 keys = 64 bytes = 4 chunks of 16 B; chunk index inside the 128-byte row: ((c % 64) / 8) + q
+                unsigned char* prow = sP + (c >> 6) * FA_TILE_BYTES + r * 128;
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                    const int ch = ((c & 63) >> 3) + qd;
+                    *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
+                }
+            };
+            if (VAR & 1) {
+                uint32_t va[32], vb[32];
+                fa_tmem_ld32(tmem_S + lane_off, va);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); chunk(va, 0);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); chunk(vb, 32);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); chunk(va, 64);
+                fa_tmem_wait_ld(); chunk(vb, 96);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < FA_BK; c += 32) {
+                    uint32_t v[32];
+                    fa_tmem_ld32(tmem_S + lane_off + c, v);
+                    fa_tmem_wait_ld();
+                    chunk(v, c);
+                }
+            }
+            return lsum0 + lsum1;
+        };
+
+        for (int j = 0; j < n_tiles; ++j) {
+            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
+            fa_fence_after();
+            const int valid = S - j * FA_BK;            // keys >= valid are padding
+            const bool full_tile = valid >= FA_BK;      // only the last key tile of a clip is masked (warp-uniform)
+            const float m_new = fmaxf(m_run, max_pass(valid, full_tile));
             const float scale = fa_ex2((m_run - m_new) * LOG2E);    // 0 on the first tile (m_run = -inf)
-            const float mneg = -m_new * LOG2E;
             // the previous P V must have finished reading P before it is overwritten, and O_tile(j-1) is folded in
             if (j > 0) {
                 fa_mbar_wait(fa_smem_u32(o_full), (j - 1) & 1);
@@ -261,42 +336,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
                     for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], scale_prev, __uint_as_float(v[i]));
                 }
             }
-            // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> shared memory (K-major, 128-byte swizzle)
-            float lsum = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < FA_BK; c += 32) {
-                uint32_t v[32];
-                fa_tmem_ld32(tmem_S + lane_off + c, v);
-                fa_tmem_wait_ld();
-                uint32_t pk[16];
-                if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg));
-                        const float p1 = fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg));
-                        lsum += p0 + p1;
-                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float p0 = (c + i < valid) ? fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg)) : 0.0f;
-                        const float p1 = (c + i + 1 < valid) ? fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)) : 0.0f;
-                        lsum += p0 + p1;
-                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                    }
-                }
-                // 32 keys = 64 bytes = 4 chunks of 16 B; chunk index inside the 128-byte row: ((c % 64) / 8) + q
-                unsigned char* prow = sP + (c >> 6) * FA_TILE_BYTES + r * 128;
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const int chunk = ((c & 63) >> 3) + qd;
-                    *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
-                        make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-                }
-            }
+            const float lsum = exp_pass(-m_new * LOG2E, valid, full_tile);
             l_run = l_run * scale + lsum;
             m_run = m_new;
             scale_prev = scale;
@@ -358,7 +398,8 @@ int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* o
             return TW_E_CUDA;
         }
         g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     }
     const int d = H * FA_D;
     if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (d % 8)) {
@@ -384,7 +425,11 @@ int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* o
         cached_ptr = qkv; cached_rows = rows; cached_cols = cols;
     }
     dim3 grid(ceil_div(S, FA_BQ), H, B);
-    encoder_attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
+    static const int variant = getenv("TWB200_FA_VARIANT") ? atoi(getenv("TWB200_FA_VARIANT")) : 1;
+    if (variant == 0)
+        encoder_attention_tc_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
+    else
+        encoder_attention_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }
