@@ -154,6 +154,18 @@ TW_API int tw_last_stage_ms(tw_model* m, float out_ms[6]);
  * accumulated samples (either pointer may be NULL), then enables/disables sampling for later calls. */
 TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch);
 
+/* Teacher forward of the distillation step: logits of EVERY position of decoder_input_ids in one batched decoder pass.
+ * Replaces teacher_model(encoder_outputs=..., labels=...) / teacher_model(**batch) followed by `.logits`
+ * (ref knowledge-distillation/run_distillation.py:1543-1577; HF WhisperForConditionalGeneration.forward,
+ * modeling_whisper.py:1000-1100 with the decoder of :691-798 under the causal mask).
+ *   enc_out            device, model dtype, [B, 1500, d_model] (output of tw_encode)
+ *   decoder_input_ids  device int32 [B, T], 1 <= T <= max_target_positions (HF shift_tokens_right is done by the caller)
+ *   logits             device float32 [B*T, ld_logits], ld_logits >= vocab and a multiple of 4 (16-byte row pitch); columns
+ *                      >= vocab are not written.  fp32 like HF's `.logits.float()`.
+ * Uses the encoder workspace: must not overlap a tw_encode / tw_transcribe_host call on another stream. */
+TW_API int tw_decoder_logits(tw_model* m, const void* enc_out, int B, const int32_t* decoder_input_ids, int T, float* logits,
+                             int64_t ld_logits, void* stream);
+
 /* Test / profiling switch (calling thread): the tw_debug_* attention entry points use the small-footprint kernel
  * variants of the split decode (3-stage K|V stream, 64-register self-attention). */
 TW_API void tw_debug_set_lite(int on);

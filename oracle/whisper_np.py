@@ -126,9 +126,11 @@ class DecoderState:
         self.pos = 0
 
 
-def decoder_forward(W, tokens, state: DecoderState, xkv, heads, n_layers):
-    """tokens [Tq] int -> logits of the last position [V] f32.  HF: WhisperDecoder.forward :691-798,
-    layer :449-507, tied proj_out :1081, logits[:, -1].float() (generation/utils.py:2762)."""
+def decoder_forward(W, tokens, state: DecoderState, xkv, heads, n_layers, all_positions=False):
+    """tokens [Tq] int -> logits of the last position [V] f32 (or of every position [Tq, V] with all_positions: the
+    teacher-forced full-sequence pass of the distillation step, ref knowledge-distillation/run_distillation.py:1543-1577).
+    HF: WhisperDecoder.forward :691-798, layer :449-507, tied proj_out :1081, logits[:, -1].float()
+    (generation/utils.py:2762)."""
     p = "model.decoder."
     tq = len(tokens)
     h = W[p + "embed_tokens.weight"][tokens] + W[p + "embed_positions.weight"][state.pos:state.pos + tq]
@@ -148,8 +150,28 @@ def decoder_forward(W, tokens, state: DecoderState, xkv, heads, n_layers):
         m = layer_norm(h, W[lp + "final_layer_norm.weight"], W[lp + "final_layer_norm.bias"])
         h = h + linear(gelu(linear(m, W[lp + "fc1.weight"], W[lp + "fc1.bias"])), W[lp + "fc2.weight"], W[lp + "fc2.bias"])
     state.pos += tq
+    if all_positions:
+        h = layer_norm(h, W[p + "layer_norm.weight"], W[p + "layer_norm.bias"])
+        return (h @ W[p + "embed_tokens.weight"].T).astype(np.float32)
     h = layer_norm(h[-1:], W[p + "layer_norm.weight"], W[p + "layer_norm.bias"])
     return (h @ W[p + "embed_tokens.weight"].T)[0].astype(np.float32)
+
+
+def teacher_logits(W, enc_out, decoder_input_ids, heads, n_layers):
+    """Logits [T, V] of every position of one row of decoder_input_ids [T] (causal mask, no cache):
+    WhisperForConditionalGeneration.forward(...).logits of HF (modeling_whisper.py:1000-1100)."""
+    xkv = cross_kv(W, enc_out, n_layers)
+    return decoder_forward(W, np.asarray(decoder_input_ids), DecoderState(n_layers), xkv, heads, n_layers, all_positions=True)
+
+
+def shift_tokens_right(labels, pad_token_id, decoder_start_token_id):
+    """HF shift_tokens_right (modeling_whisper.py:67-81)."""
+    labels = np.asarray(labels)
+    out = np.zeros_like(labels)
+    out[:, 1:] = labels[:, :-1]
+    out[:, 0] = decoder_start_token_id
+    out[out == -100] = pad_token_id
+    return out
 
 
 def log_softmax(x):

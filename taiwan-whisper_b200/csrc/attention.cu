@@ -26,20 +26,26 @@ struct EaSmem {
     float m[EA_BQ], l[EA_BQ], scale[EA_BQ];
 };
 
+// General form: Sq queries per clip (rows of q, pitch q_ld) against Sk keys / values per clip (rows of k and v, pitch
+// kv_ld); causal = key index <= query index (decoder self-attention over a full token sequence).  The encoder case is
+// q = qkv, k = qkv + d, v = qkv + 2d, pitches 3d, Sq = Sk = S.
 template <typename T>
 __global__ void __launch_bounds__(EA_THREADS)
-encoder_attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int S, int H) {
+encoder_attention_simt_kernel(const T* __restrict__ q, int64_t q_ld, const T* __restrict__ k, const T* __restrict__ v, int64_t kv_ld,
+                              T* __restrict__ out, int S, int Sk, int H, int causal) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EaSmem& sm = *reinterpret_cast<EaSmem*>(smem_raw);
     const int d = H * HD;
     const int q0 = blockIdx.x * EA_BQ, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;        // 16 x 16 threads, 4 x 4 outputs each
-    const T* base = qkv + (int64_t)b * S * 3 * d;
+    const T* qbase = q + (int64_t)b * S * q_ld;
+    const T* kbase = k + (int64_t)b * Sk * kv_ld;
+    const T* vbase = v + (int64_t)b * Sk * kv_ld;
 
     for (int i = tid; i < EA_BQ * HD; i += EA_THREADS) {
         const int r = i / HD, c = i % HD;
-        sm.q[r][c] = (q0 + r < S) ? to_f32(base[(int64_t)(q0 + r) * 3 * d + h * HD + c]) : 0.0f;
+        sm.q[r][c] = (q0 + r < S) ? to_f32(qbase[(int64_t)(q0 + r) * q_ld + h * HD + c]) : 0.0f;
     }
     if (tid < EA_BQ) {
         sm.m[tid] = -INFINITY;
@@ -51,14 +57,15 @@ encoder_attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[i][j] = 0.0f;
 
-    for (int k0 = 0; k0 < S; k0 += EA_BK) {
+    const int k_end = causal ? min(Sk, q0 + EA_BQ) : Sk;      // causal: key tiles past the last query of the block are all masked
+    for (int k0 = 0; k0 < k_end; k0 += EA_BK) {
         __syncthreads();
         for (int i = tid; i < EA_BK * HD; i += EA_THREADS) {
             const int r = i / HD, c = i % HD;
-            const bool ok = k0 + r < S;
-            const int64_t row = (int64_t)(k0 + r) * 3 * d;
-            sm.k[r][c] = ok ? to_f32(base[row + d + h * HD + c]) : 0.0f;
-            sm.v[r][c] = ok ? to_f32(base[row + 2 * d + h * HD + c]) : 0.0f;
+            const bool ok = k0 + r < Sk;
+            const int64_t row = (int64_t)(k0 + r) * kv_ld;
+            sm.k[r][c] = ok ? to_f32(kbase[row + h * HD + c]) : 0.0f;
+            sm.v[r][c] = ok ? to_f32(vbase[row + h * HD + c]) : 0.0f;
         }
         __syncthreads();
         // S tile = Q K^T, 4x4 per thread (rows ty*4.., cols tx*4..)
@@ -82,7 +89,10 @@ encoder_attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, in
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sm.s[ty * 4 + i][tx * 4 + j] = (k0 + tx * 4 + j < S) ? acc[i][j] : -INFINITY;
+            for (int j = 0; j < 4; ++j) {
+                const int kc = k0 + tx * 4 + j;
+                sm.s[ty * 4 + i][tx * 4 + j] = (kc < Sk && !(causal && kc > q0 + ty * 4 + i)) ? acc[i][j] : -INFINITY;
+            }
         __syncthreads();
         // online softmax: warp w handles rows w*8 .. w*8+7, lanes cover 64 columns (2 each)
         {
@@ -138,15 +148,25 @@ encoder_attention_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, in
 }
 
 template <typename T>
-void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStream_t st) {
+void attention_simt(const T* q, int64_t q_ld, const T* k, const T* v, int64_t kv_ld, T* out, int B, int Sq, int Sk, int H, bool causal,
+                    cudaStream_t st) {
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
         cudaFuncSetAttribute(encoder_attention_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EaSmem));
         attr_set[which] = true;
     }
-    dim3 grid(ceil_div(S, EA_BQ), H, B);
-    encoder_attention_simt_kernel<T><<<grid, EA_THREADS, sizeof(EaSmem), st>>>(qkv, out, S, H);
+    dim3 grid(ceil_div(Sq, EA_BQ), H, B);
+    encoder_attention_simt_kernel<T><<<grid, EA_THREADS, sizeof(EaSmem), st>>>(q, q_ld, k, v, kv_ld, out, Sq, Sk, H, causal ? 1 : 0);
+}
+template void attention_simt<float>(const float*, int64_t, const float*, const float*, int64_t, float*, int, int, int, int, bool, cudaStream_t);
+template void attention_simt<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, const __nv_bfloat16*, int64_t,
+                                            __nv_bfloat16*, int, int, int, int, bool, cudaStream_t);
+
+template <typename T>
+void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStream_t st) {
+    const int d = H * HD;
+    attention_simt<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, out, B, S, S, H, false, st);
 }
 template void encoder_attention_simt<float>(const float*, float*, int, int, int, cudaStream_t);
 template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, cudaStream_t);

@@ -217,6 +217,26 @@ template void embed_tokens<float>(const int32_t*, const float*, const float*, co
 template void embed_tokens<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, const int32_t*, float*, int, int,
                                           cudaStream_t);
 
+// ---- full token sequences (teacher-forced decoder pass): row = clip * Tn + position; ids outside the vocabulary (the -100 of
+// HF label tensors must be replaced by the caller) are clamped so that the gather stays in bounds
+template <typename T>
+__global__ void embed_seq_kernel(const int32_t* __restrict__ tok, const T* __restrict__ E, const T* __restrict__ P,
+                                 float* __restrict__ x, int Tn, int d, int vocab) {
+    const int row = blockIdx.x;
+    int t = tok[row];
+    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);
+    const int pos = row % Tn;
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[(int64_t)row * d + i] = to_f32(E[(int64_t)t * d + i]) + to_f32(P[(int64_t)pos * d + i]);
+}
+template <typename T>
+void embed_tokens_seq(const int32_t* tok, const T* E, const T* P, float* x, int B, int Tn, int d, int vocab, cudaStream_t st) {
+    embed_seq_kernel<T><<<B * Tn, 256, 0, st>>>(tok, E, P, x, Tn, d, vocab);
+}
+template void embed_tokens_seq<float>(const int32_t*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
+template void embed_tokens_seq<__nv_bfloat16>(const int32_t*, const __nv_bfloat16*, const __nv_bfloat16*, float*, int, int, int, int,
+                                              cudaStream_t);
+
 // ---- self-attention KV cache append: cache[b][pos][0:2d] = qkv[b][d:3d]
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ d_step, int d,

@@ -73,6 +73,9 @@ constexpr int STEP_POS = 0, STEP_P = 1, STEP_STRIDE = 2, STEP_TAP = 3, STEP_PROM
 // x[b] = E[tok[b]] + P[pos]   (f32 residual stream)
 template <typename T>
 void embed_tokens(const int32_t* tok, const T* E, const T* P, const int32_t* d_step, float* x, int B, int d, cudaStream_t st);
+// full token sequences: x[b*T + t] = E[tok[b*T + t]] + P[t]
+template <typename T>
+void embed_tokens_seq(const int32_t* tok, const T* E, const T* P, float* x, int B, int Tn, int d, int vocab, cudaStream_t st);
 // cache[b][pos][0:2d] = qkv[b][d:3d]
 template <typename T>
 void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st);
@@ -83,6 +86,12 @@ void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 // encoder self-attention on qkv T [B*S, 3d] (q pre-scaled), S keys per clip, out T [B*S, d]
 template <typename T>
 void encoder_attention_simt(const T* qkv, T* out, int B, int S, int H, cudaStream_t st);
+// general CUDA-core attention: Sq queries per clip (q rows, pitch q_ld) x Sk keys/values per clip (k / v rows, pitch kv_ld),
+// optional causal mask; out T [B*Sq, d].  Used by the full-sequence decoder pass (teacher logits) for the causal
+// self-attention and the cross-attention over the K|V store.
+template <typename T>
+void attention_simt(const T* q, int64_t q_ld, const T* k, const T* v, int64_t kv_ld, T* out, int B, int Sq, int Sk, int H, bool causal,
+                    cudaStream_t st);
 // tcgen05 flash attention (attention_tc.cu), bf16 only
 int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st);
 // decode attention (1 query per clip) over kv rows [Tk][2d] (K|V), clip stride kv_clip_stride elements.

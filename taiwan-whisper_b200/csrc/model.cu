@@ -442,6 +442,44 @@ int cross_kv_impl(tw_model* m, const void* enc_out, int B, cudaStream_t st) {
     return TW_OK;
 }
 
+// Full-sequence (teacher-forced) decoder pass: logits for every position of decoder_input_ids [B, Tn] in one batched
+// pass at M = B * Tn rows — the teacher forward of the distillation step (ref knowledge-distillation/run_distillation.py:
+// 1543-1577: teacher_model(encoder_outputs=..., labels=...) / teacher_model(**batch); HF WhisperDecoder.forward
+// modeling_whisper.py:691-798 with the causal mask, WhisperForConditionalGeneration.forward :1081).  Reuses the GEMM /
+// LayerNorm kernels of the encoder at these row counts and the encoder's workspace (both passes are never in flight
+// together); attention runs on the general CUDA-core kernel (causal over the Tn tokens, then over the K|V store).
+template <typename T>
+int decoder_logits_impl(tw_model* m, int B, const int32_t* ids, int Tn, float* logits, int64_t ld_logits, cudaStream_t st) {
+    const tw_model_desc& D = m->desc;
+    tw_ctx* ctx = m->ctx;
+    const int d = D.d_model, V = D.vocab, H = D.heads, M = B * Tn;
+    float* x = m->ws_x;
+    T* xn = (T*)m->ws_xn; T* qkv = (T*)m->ws_a2qkv; T* att = (T*)m->ws_att; T* hmid = (T*)m->ws_hmid; T* q = (T*)m->ws_h0;
+    const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
+    embed_tokens_seq<T>(ids, (const T*)m->embed, (const T*)m->dec_pos, x, B, Tn, d, V, st);
+    for (int l = 0; l < D.dec_layers; ++l) {
+        const LayerW& L = m->dec[l];
+        const T* xkv = (const T*)m->xkv + l * cross_layer;
+        layernorm<T>(x, L.ln1_g, L.ln1_b, xn, M, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, M, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
+        attention_simt<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, att, B, Tn, Tn, H, true, st);
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, M, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+        layernorm<T>(x, L.ln2_g, L.ln2_b, xn, M, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, M, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+        attention_simt<T>(q, d, xkv, xkv + d, 2 * d, att, B, Tn, TW_N_CTX, H, false, st);
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, M, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
+        layernorm<T>(x, L.ln3_g, L.ln3_b, xn, M, d, st);
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, M, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+        TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, M, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+        ctx->launches += 5;       // 3 LN, 2 attention; the GEMMs count themselves
+    }
+    layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, M, d, st);
+    TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, M, V, d, mk_epi(EPI_F32, nullptr, logits, ld_logits), st));
+    ctx->launches += 2;           // embed, LN
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
 int upload_rules(tw_model* m, const tw_rules* R, RulesDev* out, cudaStream_t st) {
     tw_ctx* ctx = m->ctx;
     const int V = m->desc.vocab;
@@ -918,6 +956,30 @@ int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* pro
     m->ev_valid[2] = m->ev_valid[3] = m->ev_valid[4] = true;
     m->ev_valid[0] = m->ev_valid[1] = m->ev_valid[6] = false;
     return r;
+}
+
+int tw_decoder_logits(tw_model* m, const void* enc_out, int B, const int32_t* decoder_input_ids, int T, float* logits,
+                      int64_t ld_logits, void* stream) {
+    if (!check_model(m, "tw_decoder_logits")) return TW_E_INVALID;
+    tw_ctx* ctx = m->ctx;
+    if (B <= 0 || B > m->desc.max_batch || !enc_out || !decoder_input_ids || !logits) {
+        ctx->set_error(TW_E_INVALID, "tw_decoder_logits: bad batch (1..max_batch) or null buffer");
+        return TW_E_INVALID;
+    }
+    if (T < 1 || T > m->desc.max_target) {
+        // HF: the decoder has max_target_positions learned positions (modeling_whisper.py:719-745)
+        ctx->set_error(TW_E_INVALID, "tw_decoder_logits: need 1 <= T <= max_target_positions (" + std::to_string(m->desc.max_target) + ")");
+        return TW_E_INVALID;
+    }
+    if (ld_logits < m->desc.vocab || ((ld_logits * 4) % 16) || (reinterpret_cast<uintptr_t>(logits) & 15)) {
+        ctx->set_error(TW_E_INVALID, "tw_decoder_logits: logits need a 16-byte aligned base and a row pitch >= vocab that is a multiple of 4 floats");
+        return TW_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = m->desc.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, enc_out, B, st) : cross_kv_impl<float>(m, enc_out, B, st);
+    if (r != TW_OK) return r;
+    return m->desc.dtype == TW_BF16 ? decoder_logits_impl<__nv_bfloat16>(m, B, decoder_input_ids, T, logits, ld_logits, st)
+                                    : decoder_logits_impl<float>(m, B, decoder_input_ids, T, logits, ld_logits, st);
 }
 
 int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_valid_host, int B, const int32_t* prompt, int P,

@@ -405,6 +405,67 @@ class B200WhisperForConditionalGeneration:
         del keep
         return (toks, lens, tap) if tap_steps else (toks, lens)
 
+    def decoder_logits(self, enc_out: torch.Tensor, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+        """enc_out [B,1500,d] + decoder_input_ids [B,T] -> fp32 logits [B,T,V] of every position in ONE batched decoder pass
+        (tw_decoder_logits).  The returned tensor is a view whose row pitch is V rounded up to 4 floats."""
+        if decoder_input_ids.dim() != 2:
+            raise ValueError("decoder_input_ids must be [batch, target_length]")
+        B, T = decoder_input_ids.shape
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
+        if T < 1 or T > self.shape.max_target:
+            raise ValueError(f"decoder_input_ids length {T} must be in 1..max_target_positions ({self.shape.max_target})")
+        enc_out = enc_out.to(self.device, self.dtype).contiguous()
+        if enc_out.shape != (B, 1500, self.shape.d_model):
+            raise ValueError(f"encoder output must be [{B}, 1500, {self.shape.d_model}], got {tuple(enc_out.shape)}")
+        ids = decoder_input_ids.to(self.device, torch.int32).contiguous()
+        V = self.shape.vocab
+        ld = (V + 3) // 4 * 4
+        buf = torch.empty((B * T, ld), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.ctx.lib.tw_decoder_logits(self.handle, enc_out.data_ptr(), B, ids.data_ptr(), T, buf.data_ptr(), ld,
+                                                          _stream_ptr(self.device)))
+        return buf.view(B, T, ld)[:, :, :V]
+
+    def shift_tokens_right(self, labels: torch.Tensor) -> torch.Tensor:
+        """HF shift_tokens_right (modeling_whisper.py:67-81): prepend decoder_start_token_id, drop the last label, -100 -> pad."""
+        start = int(self.config.decoder_start_token_id)
+        pad = int(self.config.pad_token_id)
+        shifted = labels.new_zeros(labels.shape)
+        shifted[:, 1:] = labels[:, :-1].clone()
+        shifted[:, 0] = start
+        shifted.masked_fill_(shifted == -100, pad)
+        return shifted
+
+    @torch.no_grad()
+    def forward(self, input_features=None, *, encoder_outputs=None, decoder_input_ids=None, labels=None, **kwargs):
+        """The teacher call of the distillation step (ref knowledge-distillation/run_distillation.py:1543-1577):
+        `teacher_model(**batch)` with input_features / labels / decoder_input_ids, or
+        `teacher_model(encoder_outputs=BaseModelOutput(h), labels=labels)` when the frozen encoder is shared.
+        Returns an object with `.logits` [B,T,V] (fp32) and `.encoder_last_hidden_state`; no loss (the reference never
+        reads the teacher's)."""
+        from types import SimpleNamespace
+        for k, v in kwargs.items():
+            if v is not None and k not in ("attention_mask", "decoder_attention_mask", "return_dict", "use_cache"):
+                raise NotImplementedError(f"forward(): argument {k!r} is not supported by the B200 teacher path")
+        if kwargs.get("decoder_attention_mask") is not None:
+            raise NotImplementedError("forward(): decoder_attention_mask is not supported (the reference passes none)")
+        if encoder_outputs is not None:
+            enc = encoder_outputs[0] if isinstance(encoder_outputs, (tuple, list)) else getattr(encoder_outputs, "last_hidden_state", encoder_outputs)
+        elif input_features is not None:
+            feats = input_features if torch.is_tensor(input_features) else torch.as_tensor(np.asarray(input_features))
+            enc = self.encode(feats.float())
+        else:
+            raise ValueError("You have to specify either input_features or encoder_outputs")
+        if decoder_input_ids is None:
+            if labels is None:
+                raise ValueError("You have to specify either decoder_input_ids or labels")
+            decoder_input_ids = self.shift_tokens_right(labels if torch.is_tensor(labels) else torch.as_tensor(labels))
+        logits = self.decoder_logits(enc, decoder_input_ids)
+        return SimpleNamespace(logits=logits, encoder_last_hidden_state=enc, loss=None)
+
+    __call__ = forward
+
     def transcribe_pcm(self, pcm_host: torch.Tensor, max_length: int, return_timestamps: bool = False, language="zh",
                        task="transcribe", n_valid: Optional[torch.Tensor] = None, out_tokens: Optional[torch.Tensor] = None,
                        out_lengths: Optional[torch.Tensor] = None):

@@ -61,6 +61,38 @@ def golden_model(shape_name, max_length=48):
     np.savez_compressed(os.path.join(OUT, f"model_{shape_name}.npz"), **rec)
 
 
+def teacher_labels(vocab, n_rows=2, T=24, seed=77):
+    """Label rows like the distillation collator makes them (ref knowledge-distillation/run_distillation.py:470-512):
+    prompt + text tokens, right-padded with -100."""
+    ids = token_ids(vocab)
+    rng = np.random.default_rng(seed + vocab)
+    lab = np.full((n_rows, T), -100, dtype=np.int64)
+    for b in range(n_rows):
+        n = T - 5 * b
+        row = [ids.lang_to_id["<|zh|>"], ids.transcribe, ids.notimestamps] + rng.integers(0, 50000, n - 4).tolist() + [ids.eos]
+        lab[b, :n] = row
+    return lab
+
+
+def golden_teacher(shape_name):
+    """HF teacher forward: model(input_features, labels).logits — the call of the distillation step
+    (ref knowledge-distillation/run_distillation.py:1543-1577)."""
+    sh = SHAPES[shape_name]
+    model = hf_ref.build_hf_model(sh, seed=1234)
+    fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
+    feats = hf_ref.hf_features(fe, dequantise(synth_batch(0, 2)))
+    labels = teacher_labels(sh.vocab)
+    with torch.no_grad():
+        out = model(input_features=torch.as_tensor(feats), labels=torch.as_tensor(labels))
+    lg = out.logits.float().numpy()
+    from transformers.models.whisper.modeling_whisper import shift_tokens_right
+    dec_ids = shift_tokens_right(torch.as_tensor(labels), model.config.pad_token_id, model.config.decoder_start_token_id).numpy()
+    rec = {"versions": VERS, "labels": labels, "decoder_input_ids": dec_ids,
+           "logits_sub": lg[:, :, ::97].copy(), "argmax": lg.argmax(-1),
+           "row_norm": np.linalg.norm(lg.astype(np.float64), axis=-1)}
+    np.savez_compressed(os.path.join(OUT, f"teacher_{shape_name}.npz"), **rec)
+
+
 def rules_case_logits(vocab, ci, variant, tsb):
     """Logits of a rules case are regenerated from (vocab, case, variant) — not stored."""
     rng = np.random.default_rng(vocab * 1000 + ci * 10 + variant)
@@ -112,9 +144,15 @@ def golden_rules():
 
 
 if __name__ == "__main__":
-    golden_logmel()
-    golden_model("tiny")
-    golden_model("micro128")
-    golden_rules()
+    if "teacher" in sys.argv[1:]:          # only the fixtures added later (the others are unchanged)
+        golden_teacher("tiny")
+        golden_teacher("micro128")
+    else:
+        golden_logmel()
+        golden_model("tiny")
+        golden_model("micro128")
+        golden_rules()
+        golden_teacher("tiny")
+        golden_teacher("micro128")
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -14,7 +14,7 @@ import torch
 from oracle import logmel_np
 from taiwan_whisper_b200.configs import SHAPES, token_ids
 from taiwan_whisper_b200.synth import dequantise, edge_case_clips, synth_batch
-from tests.helpers import prompt_ids
+from tests.helpers import default_rules, prompt_ids
 
 pytestmark = pytest.mark.gpu
 
@@ -451,6 +451,87 @@ def test_split_decode_bf16_teacher_forced(shape_name, nsplit):
     assert solid > 0 and solid_agree / solid >= 0.995
     assert agree / (3 * n_gen) >= 0.80
     assert free.shape == toks.shape and (free >= 0).all() and (free < sh.vocab).all()
+
+
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+def test_teacher_logits_fp32_vs_oracle_and_golden(golden_dir, shape_name):
+    """tw_decoder_logits (teacher forward of the distillation step) in fp32 check mode: every position's logits vs the
+    oracle and vs the HF golden fixture."""
+    _cuda()
+    from tests.gpu_common import b200_model, hf_model
+    from oracle import whisper_np
+    from tests.helpers import weights_np
+    g = np.load(os.path.join(golden_dir, f"teacher_{shape_name}.npz"))
+    sh = SHAPES[shape_name]
+    m = b200_model(shape_name, "f32")
+    mel = logmel_np.log_mel(dequantise(synth_batch(0, 2)), sh.n_mel)
+    out = m(input_features=torch.from_numpy(mel), labels=torch.from_numpy(g["labels"]))
+    lg = out.logits.cpu().numpy()
+    assert lg.shape == (2, g["labels"].shape[1], sh.vocab) and lg.dtype == np.float32
+    assert np.abs(lg[:, :, ::97] - g["logits_sub"]).max() < 1e-4
+    W = weights_np(hf_model(shape_name))
+    enc = out.encoder_last_hidden_state.float().cpu().numpy()
+    ref = whisper_np.teacher_logits(W, enc[0], g["decoder_input_ids"][0], sh.heads, sh.dec_layers)
+    assert np.abs(lg[0] - ref).max() < 1e-4
+    # the shared-encoder form of the call: teacher_model(encoder_outputs=..., labels=...)
+    out2 = m(encoder_outputs=(out.encoder_last_hidden_state,), labels=torch.from_numpy(g["labels"]))
+    assert torch.equal(out2.logits, out.logits)
+
+
+@pytest.mark.parametrize("shape_name,T", [("tiny", 24), ("micro128", 70)])
+def test_teacher_logits_bf16(shape_name, T):
+    """bf16 product path (tcgen05 GEMMs at M = B*T rows, TMA-stored fp32 logits with a padded row pitch): relative L2 of
+    the logits vs the fp32 oracle, and the full-sequence pass must agree with the KV-cached step decoder fed the same
+    tokens (same kernels' arithmetic, different schedule)."""
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run, hf_model
+    from oracle import whisper_np
+    from tests.helpers import weights_np
+    sh = SHAPES[shape_name]
+    P = prompt_ids(sh.vocab, False)
+    pcm, mel, ora = oracle_run(shape_name, 3, 64, False)
+    rows = [(P + o["tokens"] + [0] * T)[:T] for o in ora]
+    dec = torch.tensor(rows, dtype=torch.int64)
+    m = b200_model(shape_name, "bf16")
+    enc = m.encode(torch.from_numpy(mel).cuda())
+    lg = m.decoder_logits(enc, dec).cpu().numpy()
+    assert lg.shape == (3, T, sh.vocab)
+    W = weights_np(hf_model(shape_name))
+    for b in range(3):
+        ref = whisper_np.teacher_logits(W, ora[b]["enc"], rows[b], sh.heads, sh.dec_layers)
+        rel = np.linalg.norm(lg[b] - ref) / np.linalg.norm(ref)
+        assert rel < 2e-2, (b, rel)
+    # teacher-forced step decode: position len(P)-1+s of the full pass predicts generated token s
+    n_gen = T - len(P)
+    forced = torch.tensor([(o["tokens"] + [0] * T)[:n_gen] for o in ora], dtype=torch.int32)
+    toks, lens = m.decode(enc, P, T, False, forced=forced)
+    toks = toks.cpu().numpy()
+    r = default_rules(sh.vocab, False)
+    agree = total = 0
+    for b in range(3):
+        for s in range(min(n_gen, len(ora[b]["tokens"]))):
+            row = lg[b, len(P) - 1 + s].copy()
+            row[np.asarray(r["suppress"])] = -np.inf
+            if s == 0:
+                row[np.asarray(r["begin_suppress"])] = -np.inf
+            top2 = np.sort(row)[-2:]
+            if top2[1] - top2[0] > 0.02:
+                total += 1
+                agree += int(np.argmax(row) == toks[b, s])
+    assert total > 20 and agree / total >= 0.995, (agree, total)
+
+
+def test_teacher_logits_argument_errors():
+    _cuda()
+    from tests.gpu_common import b200_model
+    m = b200_model("tiny", "f32")
+    enc = torch.zeros((1, 1500, 384), device="cuda")
+    with pytest.raises(ValueError):
+        m.decoder_logits(enc, torch.zeros((1, 449), dtype=torch.int64))          # > max_target_positions
+    with pytest.raises(ValueError):
+        m()                                                                        # neither features nor encoder outputs
+    with pytest.raises(ValueError):
+        m(encoder_outputs=(enc,))                                                  # neither ids nor labels
 
 
 def test_transcribe_host_path_matches_generate():

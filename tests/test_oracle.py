@@ -127,3 +127,25 @@ def test_decoder_kv_cache_equals_full_recompute():
     for t in toks[4:]:
         inc = whisper_np.decoder_forward(W, np.asarray([t]), st, xkv, sh.heads, sh.dec_layers)
     assert np.abs(full - inc).max() < 1e-5
+
+
+@pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
+def test_teacher_logits_oracle_vs_golden(golden_dir, shape_name):
+    """Full-sequence (teacher-forced) decoder logits of the oracle vs HF model(input_features, labels).logits
+    (the teacher call of ref knowledge-distillation/run_distillation.py:1543-1577)."""
+    g = np.load(os.path.join(golden_dir, f"teacher_{shape_name}.npz"))
+    sh = SHAPES[shape_name]
+    hf = hf_ref.build_hf_model(sh, seed=1234)
+    W = weights_np(hf)
+    mel = logmel_np.log_mel(dequantise(synth_batch(0, 2)), sh.n_mel)
+    dec = whisper_np.shift_tokens_right(g["labels"], hf.config.pad_token_id, hf.config.decoder_start_token_id)
+    assert np.array_equal(dec, g["decoder_input_ids"])
+    for b in range(2):
+        enc = whisper_np.encoder_forward(W, mel[b], sh.heads, sh.enc_layers)
+        lg = whisper_np.teacher_logits(W, enc, dec[b], sh.heads, sh.dec_layers)
+        assert lg.shape == (dec.shape[1], sh.vocab)
+        assert np.abs(lg[:, ::97] - g["logits_sub"][b]).max() < 1e-4
+        assert np.abs(np.linalg.norm(lg.astype(np.float64), axis=-1) - g["row_norm"][b]).max() < 1e-3
+        top2 = np.sort(lg, axis=-1)[:, -2:]
+        solid = (top2[:, 1] - top2[:, 0]) > 1e-3
+        assert np.array_equal(lg.argmax(-1)[solid], g["argmax"][b][solid])
