@@ -166,6 +166,13 @@ TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, d
 TW_API int tw_decoder_logits(tw_model* m, const void* enc_out, int B, const int32_t* decoder_input_ids, int T, float* logits,
                              int64_t ld_logits, void* stream);
 
+/* Test / profiling entry point: attention of the full-sequence decoder pass.  Sq query rows per clip in q (row pitch q_ld
+ * elements, head h at column q_col0 + 64 h) against Sk key / value rows per clip in kv (pitch kv_ld, K at k_col0 + 64 h, V at
+ * v_col0 + 64 h); causal != 0 masks keys later than the query (needs Sq == Sk).  out [B*Sq, 64 H].  impl 1 = tcgen05 kernel
+ * (bf16), 0 = CUDA-core kernel. */
+TW_API int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_col0, const void* kv, int64_t kv_ld, int k_col0,
+                              int v_col0, void* out, int B, int Sq, int Sk, int H, int dtype, int impl, int causal, void* stream);
+
 /* Test / profiling switch (calling thread): the tw_debug_* attention entry points use the small-footprint kernel
  * variants of the split decode (3-stage K|V stream, 64-register self-attention). */
 TW_API void tw_debug_set_lite(int on);

@@ -100,7 +100,8 @@ __host__ __device__ constexpr uint32_t fa_idesc(int M, int N, int b_mn_major) {
 // producer / MMA-issuer waits — none of them faster.
 template <int VAR>
 __global__ void __launch_bounds__(FA_THREADS, 2)
-encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bfloat16* __restrict__ out, int S, int H) {
+encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                            __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
     extern __shared__ unsigned char fa_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* sQ = smem;
@@ -122,11 +123,15 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int d = H * FA_D;
     const int q0 = qb * FA_BQ;
-    const int n_tiles = (S + FA_BK - 1) / FA_BK;
-    const int row_base = b * S;                       // first row of this clip in the [B*S, 3d] matrix
+    // S queries per clip (rows of map_q), Sk keys / values per clip (rows of map_kv); causal: key index <= query index, so
+    // query block qb only visits key tiles 0..qb (FA_BQ == FA_BK)
+    const int n_tiles = causal ? min((Sk + FA_BK - 1) / FA_BK, qb + 1) : (Sk + FA_BK - 1) / FA_BK;
+    const int row_base = b * S;                       // first query row of this clip
+    const int kv_base = b * Sk;                       // first key / value row of this clip
 
     if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qkv) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
         fa_mbar_init(fa_smem_u32(q_full), 1);
         for (int i = 0; i < 2; ++i) {
             fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
@@ -155,17 +160,17 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
         // ===================== TMA producer =====================
         if (lane == 0) {
             fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
-            fa_tma_load_2d(&map_qkv, fa_smem_u32(q_full), fa_smem_u32(sQ), h * FA_D, row_base + q0);
+            fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
                 fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
                 fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_qkv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), d + h * FA_D,
-                               row_base + j * FA_BK);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), k_col0 + h * FA_D,
+                               kv_base + j * FA_BK);
                 fa_mbar_wait(fa_smem_u32(&v_empty[0]), (j & 1) ^ 1);
                 fa_mbar_expect_tx(fa_smem_u32(&v_full[0]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_qkv, fa_smem_u32(&v_full[0]), fa_smem_u32(sV), 2 * d + h * FA_D, row_base + j * FA_BK);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[0]), fa_smem_u32(sV), v_col0 + h * FA_D, kv_base + j * FA_BK);
             }
         }
     } else if (warp == 5) {
@@ -319,8 +324,10 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, __nv_bf
         for (int j = 0; j < n_tiles; ++j) {
             fa_mbar_wait(fa_smem_u32(s_full), j & 1);
             fa_fence_after();
-            const int valid = S - j * FA_BK;            // keys >= valid are padding
-            const bool full_tile = valid >= FA_BK;      // only the last key tile of a clip is masked (warp-uniform)
+            // keys >= valid are padding (the tail of the clip) or, under the causal mask, later than this row's query
+            const int valid = causal ? min(Sk - j * FA_BK, q0 + r - j * FA_BK + 1) : Sk - j * FA_BK;
+            // only the last key tile of a clip / the diagonal tile is masked (warp-uniform)
+            const bool full_tile = (Sk - j * FA_BK >= FA_BK) && !(causal && j == qb);
             const float m_new = fmaxf(m_run, max_pass(valid, full_tile));
             const float scale = fa_ex2((m_run - m_new) * LOG2E);    // 0 on the first tile (m_run = -inf)
             // the previous P V must have finished reading P before it is overwritten, and O_tile(j-1) is folded in
@@ -388,7 +395,40 @@ typedef CUresult (*FaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static FaEncodeTiledFn g_fa_encode = nullptr;
 
-int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st) {
+static int fa_map(tw_ctx* ctx, const __nv_bfloat16* ptr, int rows, int64_t ld, CUtensorMap* out) {
+    struct Entry { const void* ptr; int rows; int64_t ld; CUtensorMap map; };
+    static Entry cache[8];
+    static int n_cached = 0, next = 0;
+    for (int i = 0; i < n_cached; ++i)
+        if (cache[i].ptr == ptr && cache[i].rows == rows && cache[i].ld == ld) { *out = cache[i].map; return TW_OK; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) {
+        ctx->set_error(TW_E_UNSUPPORTED, "attention_tc: operands must be 16-byte aligned with a row pitch that is a multiple of 8 elements");
+        return TW_E_UNSUPPORTED;
+    }
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_fa_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        ctx->set_error(TW_E_CUDA, "attention_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        return TW_E_CUDA;
+    }
+    Entry& e = cache[next];
+    e.ptr = ptr; e.rows = rows; e.ld = ld; e.map = m;
+    next = (next + 1) % 8;
+    if (n_cached < 8) ++n_cached;
+    *out = m;
+    return TW_OK;
+}
+
+// General form: Sq query rows per clip in q (pitch q_ld, head h at column q_col0 + 64 h) against Sk key / value rows per clip
+// in kv (pitch kv_ld, K at k_col0 + 64 h, V at v_col0 + 64 h); causal needs Sq == Sk.  out [B*Sq, 64 H].
+int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, const __nv_bfloat16* kv, int64_t kv_ld, int k_col0,
+                 int v_col0, __nv_bfloat16* out, int B, int Sq, int Sk, int H, bool causal, cudaStream_t st) {
     if (!g_fa_encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -401,37 +441,26 @@ int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* o
         TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     }
-    const int d = H * FA_D;
-    if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (d % 8)) {
-        ctx->set_error(TW_E_UNSUPPORTED, "encoder_attention_tc: qkv must be 16-byte aligned");
-        return TW_E_UNSUPPORTED;
+    if (causal && Sq != Sk) {
+        ctx->set_error(TW_E_INVALID, "attention_tc: the causal mask needs as many queries as keys");
+        return TW_E_INVALID;
     }
-    static const void* cached_ptr = nullptr;
-    static int cached_rows = 0, cached_cols = 0;
-    static CUtensorMap cached_map;
-    const int rows = B * S, cols = 3 * d;
-    if (cached_ptr != qkv || cached_rows != rows || cached_cols != cols) {
-        const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-        const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-        const cuuint32_t box[2] = {64, 128};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_fa_encode(&cached_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(qkv), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            ctx->set_error(TW_E_CUDA, "encoder_attention_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-            return TW_E_CUDA;
-        }
-        cached_ptr = qkv; cached_rows = rows; cached_cols = cols;
-    }
-    dim3 grid(ceil_div(S, FA_BQ), H, B);
+    CUtensorMap mq, mkv;
+    TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
+    TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv));
+    dim3 grid(ceil_div(Sq, FA_BQ), H, B);
     static const int variant = getenv("TWB200_FA_VARIANT") ? atoi(getenv("TWB200_FA_VARIANT")) : 1;
     if (variant == 0)
-        encoder_attention_tc_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
+        encoder_attention_tc_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
     else
-        encoder_attention_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(cached_map, out, S, H);
+        encoder_attention_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
+}
+
+int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st) {
+    const int d = H * FA_D;
+    return attention_tc(ctx, qkv, 3 * d, 0, qkv, 3 * d, d, 2 * d, out, B, S, S, H, false, st);
 }
 
 }  // namespace tw

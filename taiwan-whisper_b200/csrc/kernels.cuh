@@ -94,6 +94,9 @@ void attention_simt(const T* q, int64_t q_ld, const T* k, const T* v, int64_t kv
                     cudaStream_t st);
 // tcgen05 flash attention (attention_tc.cu), bf16 only
 int encoder_attention_tc(tw_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int H, cudaStream_t st);
+// the same kernel on separate query and key/value matrices, optionally causal (full-sequence decoder pass)
+int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, const __nv_bfloat16* kv, int64_t kv_ld, int k_col0,
+                 int v_col0, __nv_bfloat16* out, int B, int Sq, int Sk, int H, bool causal, cudaStream_t st);
 // decode attention (1 query per clip) over kv rows [Tk][2d] (K|V), clip stride kv_clip_stride elements.
 // q T [B, q_stride]; partial workspace f32 [decode_attention_partial_floats]; out T [B, d].
 template <typename T>

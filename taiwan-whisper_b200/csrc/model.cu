@@ -390,6 +390,25 @@ int enc_attention<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* qkv, __nv_bfl
     return TW_OK;
 }
 
+// attention on separate query / key-value matrices (full-sequence decoder pass): tcgen05 kernel for bf16, CUDA-core kernel
+// for the fp32 check mode (and for bf16 with TWB200_ATTN=simt)
+template <typename T>
+int seq_attention(tw_model* m, const T* q, int64_t q_ld, int q_col0, const T* kv, int64_t kv_ld, int k_col0, int v_col0, T* out, int B,
+                  int Sq, int Sk, bool causal, cudaStream_t st);
+template <>
+int seq_attention<float>(tw_model* m, const float* q, int64_t q_ld, int q_col0, const float* kv, int64_t kv_ld, int k_col0, int v_col0,
+                         float* out, int B, int Sq, int Sk, bool causal, cudaStream_t st) {
+    attention_simt<float>(q + q_col0, q_ld, kv + k_col0, kv + v_col0, kv_ld, out, B, Sq, Sk, m->desc.heads, causal, st);
+    return TW_OK;
+}
+template <>
+int seq_attention<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* q, int64_t q_ld, int q_col0, const __nv_bfloat16* kv, int64_t kv_ld,
+                                 int k_col0, int v_col0, __nv_bfloat16* out, int B, int Sq, int Sk, bool causal, cudaStream_t st) {
+    if (m->use_tc_attn) return attention_tc(m->ctx, q, q_ld, q_col0, kv, kv_ld, k_col0, v_col0, out, B, Sq, Sk, m->desc.heads, causal, st);
+    attention_simt<__nv_bfloat16>(q + q_col0, q_ld, kv + k_col0, kv + v_col0, kv_ld, out, B, Sq, Sk, m->desc.heads, causal, st);
+    return TW_OK;
+}
+
 inline GemmEpi mk_epi(int mode, const float* bias, void* C, int64_t ldc, const float* pos = nullptr, int period = 1) {
     GemmEpi e;
     e.mode = mode; e.bias = bias; e.C = C; e.ldc = ldc; e.pos = pos; e.pos_period = period;
@@ -447,12 +466,13 @@ int cross_kv_impl(tw_model* m, const void* enc_out, int B, cudaStream_t st) {
 // 1543-1577: teacher_model(encoder_outputs=..., labels=...) / teacher_model(**batch); HF WhisperDecoder.forward
 // modeling_whisper.py:691-798 with the causal mask, WhisperForConditionalGeneration.forward :1081).  Reuses the GEMM /
 // LayerNorm kernels of the encoder at these row counts and the encoder's workspace (both passes are never in flight
-// together); attention runs on the general CUDA-core kernel (causal over the Tn tokens, then over the K|V store).
+// together); attention is the encoder's tcgen05 flash kernel on separate query / key-value matrices (causal over the Tn
+// tokens, then over the K|V store), the general CUDA-core kernel in fp32 check mode.
 template <typename T>
 int decoder_logits_impl(tw_model* m, int B, const int32_t* ids, int Tn, float* logits, int64_t ld_logits, cudaStream_t st) {
     const tw_model_desc& D = m->desc;
     tw_ctx* ctx = m->ctx;
-    const int d = D.d_model, V = D.vocab, H = D.heads, M = B * Tn;
+    const int d = D.d_model, V = D.vocab, M = B * Tn;
     float* x = m->ws_x;
     T* xn = (T*)m->ws_xn; T* qkv = (T*)m->ws_a2qkv; T* att = (T*)m->ws_att; T* hmid = (T*)m->ws_hmid; T* q = (T*)m->ws_h0;
     const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
@@ -462,11 +482,11 @@ int decoder_logits_impl(tw_model* m, int B, const int32_t* ids, int Tn, float* l
         const T* xkv = (const T*)m->xkv + l * cross_layer;
         layernorm<T>(x, L.ln1_g, L.ln1_b, xn, M, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, M, 3 * d, d, mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d), st));
-        attention_simt<T>(qkv, 3 * d, qkv + d, qkv + 2 * d, 3 * d, att, B, Tn, Tn, H, true, st);
+        TW_CHECK(seq_attention<T>(m, qkv, 3 * d, 0, qkv, 3 * d, d, 2 * d, att, B, Tn, Tn, true, st));
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, M, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         layernorm<T>(x, L.ln2_g, L.ln2_b, xn, M, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, M, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
-        attention_simt<T>(q, d, xkv, xkv + d, 2 * d, att, B, Tn, TW_N_CTX, H, false, st);
+        TW_CHECK(seq_attention<T>(m, q, d, 0, xkv, 2 * d, 0, d, att, B, Tn, TW_N_CTX, false, st));
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, M, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
         layernorm<T>(x, L.ln3_g, L.ln3_b, xn, M, d, st);
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, M, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
@@ -1108,6 +1128,24 @@ int tw_debug_encoder_attention(tw_ctx* ctx, const void* qkv, void* out, int B, i
     else
         encoder_attention_simt<float>((const float*)qkv, (float*)out, B, S, H, st);
     ctx->launches += 1;
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_col0, const void* kv, int64_t kv_ld, int k_col0, int v_col0,
+                       void* out, int B, int Sq, int Sk, int H, int dtype, int impl, int causal, void* stream) {
+    if (!ctx || !q || !kv || !out || B <= 0 || Sq <= 0 || Sk <= 0 || H <= 0) return TW_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->launches += 1;
+    if (dtype == TW_BF16 && impl == 1)
+        return attention_tc(ctx, (const __nv_bfloat16*)q, q_ld, q_col0, (const __nv_bfloat16*)kv, kv_ld, k_col0, v_col0,
+                            (__nv_bfloat16*)out, B, Sq, Sk, H, causal != 0, st);
+    if (dtype == TW_BF16)
+        attention_simt<__nv_bfloat16>((const __nv_bfloat16*)q + q_col0, q_ld, (const __nv_bfloat16*)kv + k_col0,
+                                      (const __nv_bfloat16*)kv + v_col0, kv_ld, (__nv_bfloat16*)out, B, Sq, Sk, H, causal != 0, st);
+    else
+        attention_simt<float>((const float*)q + q_col0, q_ld, (const float*)kv + k_col0, (const float*)kv + v_col0, kv_ld, (float*)out,
+                              B, Sq, Sk, H, causal != 0, st);
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

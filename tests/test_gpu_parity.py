@@ -210,6 +210,44 @@ def test_encoder_attention_kernels_vs_torch(B, S, H, impl):
     assert err < 2e-2, err                       # bf16 P and bf16 output rounding
 
 
+@pytest.mark.parametrize("B,Sq,Sk,H,causal", [(3, 70, 70, 2, True), (2, 300, 300, 2, True), (1, 128, 128, 6, True),
+                                              (3, 70, 1500, 6, False), (2, 129, 200, 2, False), (1, 448, 1500, 20, False)])
+@pytest.mark.parametrize("impl,dtype", [(0, "f32"), (0, "bf16"), (1, "bf16")])
+def test_general_attention_kernels_vs_torch(B, Sq, Sk, H, causal, impl, dtype):
+    """Attention of the full-sequence decoder pass: separate query and key/value matrices with their own row pitches and
+    column offsets (packed QKV for the causal self-attention, q vs the K|V store for the cross-attention)."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Sq + Sk + H)
+    if causal:       # packed [B*S, 3d]: q | k | v
+        qkv = (torch.randn((B * Sq, 3 * d), device="cuda", generator=g) * 0.5).to(tdt)
+        q_t, q_ld, q_col0, kv_t, kv_ld, k_col0, v_col0 = qkv, 3 * d, 0, qkv, 3 * d, d, 2 * d
+        qf = qkv[:, :d].float().view(B, Sq, H, 64)
+        kf = qkv[:, d:2 * d].float().view(B, Sk, H, 64)
+        vf = qkv[:, 2 * d:].float().view(B, Sk, H, 64)
+    else:            # q [B*Sq, d] and a K|V store [B*Sk, 2d]
+        q_t = (torch.randn((B * Sq, d), device="cuda", generator=g) * 0.5).to(tdt)
+        kv_t = (torch.randn((B * Sk, 2 * d), device="cuda", generator=g) * 0.5).to(tdt)
+        q_ld, q_col0, kv_ld, k_col0, v_col0 = d, 0, 2 * d, 0, d
+        qf = q_t.float().view(B, Sq, H, 64)
+        kf = kv_t[:, :d].float().view(B, Sk, H, 64)
+        vf = kv_t[:, d:].float().view(B, Sk, H, 64)
+    sc = torch.einsum("bqhd,bkhd->bhqk", qf, kf)
+    if causal:
+        sc = sc.masked_fill(torch.ones((Sq, Sk), device="cuda", dtype=torch.bool).triu(1), float("-inf"))
+    ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(sc, -1), vf).reshape(B * Sq, d)
+    out = torch.full((B * Sq, d), 7.0, device="cuda", dtype=tdt)
+    ctx.check(ctx.lib.tw_debug_attention(ctx.handle, q_t.data_ptr(), q_ld, q_col0, kv_t.data_ptr(), kv_ld, k_col0, v_col0, out.data_ptr(),
+                                         B, Sq, Sk, H, twlib.TW_F32 if dtype == "f32" else twlib.TW_BF16, impl, int(causal),
+                                         torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < (2e-5 if dtype == "f32" else 2e-2), err
+
+
 @pytest.mark.parametrize("Tk,B,H", [(1500, 3, 6), (1, 2, 2), (37, 5, 20), (448, 64, 2)])
 @pytest.mark.parametrize("entry", ["tw_debug_decode_attention", "tw_debug_self_attention"])
 def test_decode_attention_kernel_vs_torch(Tk, B, H, entry):
