@@ -106,6 +106,15 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def sustained_tflops():
+    """cuBLAS bf16 throughput held back to back for seconds (MEASURED_PEAKS.json) — the denominator that applies to a
+    stage timed inside a long step; the burst figure (`peaks()`) applies to a kernel timed alone."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("bf16_tflops_sustained")
+    return None
+
+
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/r01_decode_attention_stream_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, bench shape)."""
@@ -313,6 +322,7 @@ def main():
 
     if rank == 0:
         hbm, tf, which = peaks()
+        tf_sus = sustained_tflops()
         if not isinstance(stage, dict):
             stage = {}
         bytes_per_launch = B * 1500 * 2 * sh.d_model * 2          # K|V rows of one decoder layer for the batch, bf16
@@ -342,9 +352,11 @@ def main():
                 "logmel": {"bound": "hbm", "ms": stage["logmel"], "achieved_gbs": lm_bytes / stage["logmel"] / 1e6,
                            "frac": lm_bytes / stage["logmel"] / 1e6 / hbm, "h2d_ms": stage.get("h2d")},
                 "encoder": {"bound": "tensor", "ms": stage["encoder"], "achieved_tflops": enc_flops / stage["encoder"] / 1e9,
-                            "frac": enc_flops / stage["encoder"] / 1e9 / tf},
+                            "frac": enc_flops / stage["encoder"] / 1e9 / tf,
+                            "frac_of_sustained_peak": (enc_flops / stage["encoder"] / 1e9 / tf_sus) if tf_sus else None},
                 "cross_kv": {"bound": "tensor", "ms": stage["cross_kv"], "achieved_tflops": xkv_flops / stage["cross_kv"] / 1e9,
-                             "frac": xkv_flops / stage["cross_kv"] / 1e9 / tf},
+                             "frac": xkv_flops / stage["cross_kv"] / 1e9 / tf,
+                             "frac_of_sustained_peak": (xkv_flops / stage["cross_kv"] / 1e9 / tf_sus) if tf_sus else None},
                 "decode": {"bound": "hbm", "ms": stage["decode"], "achieved_gbs": dec_bytes / stage["decode"] / 1e6,
                            "frac": dec_bytes / stage["decode"] / 1e6 / hbm,
                            "note": "weights + cross-K/V + self-K/V streamed once per token"},

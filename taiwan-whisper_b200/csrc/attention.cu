@@ -186,7 +186,6 @@ template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_b
 constexpr int DA_WARPS = 8;        // consumer warps == rows per stage
 constexpr int DA_MAXSLOT = 5;      // ceil(H*8/32) with H <= 20
 constexpr int DA_PSTRIDE = HD + 2; // partial record: m, l, o[64]
-constexpr int DA_THREADS = (DA_WARPS + 1) * 32;
 constexpr int DA_MAX_STAGES = 8;
 
 __device__ __forceinline__ uint32_t da_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -247,15 +246,15 @@ struct DaPlan {
     int stages;
     size_t smem;
 };
-static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stages) {
+static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stages, int nw) {
     DaPlan p;
     int g = ceil_div(total_rows, DA_WARPS);
     if (g > sm_count) g = sm_count;
     if (g < 1) g = 1;
     p.G = g;
     p.R = ceil_div(total_rows, g);
-    const size_t stage_bytes = (size_t)DA_WARPS * 2 * H * HD * esz;
-    const size_t merge_bytes = (size_t)(DA_WARPS / 2) * H * DA_PSTRIDE * sizeof(float);
+    const size_t stage_bytes = (size_t)nw * 2 * H * HD * esz;
+    const size_t merge_bytes = (size_t)((nw + 1) / 2) * H * DA_PSTRIDE * sizeof(float);
     int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
     if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
     if (st > max_stages) st = max_stages;
@@ -265,17 +264,21 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
     return p;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(DA_THREADS, 1)
+// NW = consumer warps = rows per stage.  8 (+ the producer warp = 9 warps) is the unsplit decode; 7 (+ producer = 8 warps:
+// exactly two warps per SM sub-partition) is the split decode, where the CTA must leave registers in every sub-partition
+// for the decode-step kernels of another sub-batch (profiles/r01_split_decode.md).
+template <typename T, int NW>
+// launch bound 384 for NW = 7 only caps the registers at 168 (65536 / 384), the count the 9-warp variant uses
+__global__ void __launch_bounds__(NW == 7 ? 384 : (NW + 1) * 32, 1)
 decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                         const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
     const int row_elems = 2 * d;
-    const uint32_t stage_bytes = (uint32_t)DA_WARPS * row_elems * sizeof(T);
+    const uint32_t stage_bytes = (uint32_t)NW * row_elems * sizeof(T);
     T* ring = reinterpret_cast<T*>(da_raw);
     float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(DA_WARPS / 2) * H * DA_PSTRIDE * sizeof(float));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(((NW + 1) / 2)) * H * DA_PSTRIDE * sizeof(float));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
@@ -283,7 +286,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     pdl_trigger();
     // kv_static: the K|V store was written long before the previous kernel (cross-attention K/V of the window), so the
     // producer may start streaming it while the previous kernel (the q projection) is still running
-    if (!(kv_static && warp == DA_WARPS)) pdl_wait();
+    if (!(kv_static && warp == NW)) pdl_wait();
     if (d_tk) Tk = *d_tk + 1;
     const int64_t total = (int64_t)B * Tk;
     const int R = da_rows_per_cta(total, gridDim.x);
@@ -294,13 +297,13 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             da_mbar_init(da_smem_u32(&full_bar[s]), 1);
-            da_mbar_init(da_smem_u32(&empty_bar[s]), DA_WARPS);
+            da_mbar_init(da_smem_u32(&empty_bar[s]), NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == DA_WARPS) {
+    if (warp == NW) {
         // ===================== producer =====================
         if (lane == 0) {
             // the K|V store is streamed once per launch and is far larger than L2: mark the lines evict-first
@@ -313,8 +316,8 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                 const int b = (int)(r / Tk);
                 const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
                 const T* src_clip = kv + (int64_t)b * kv_clip_stride;
-                for (int64_t r0 = r; r0 < seg_end; r0 += DA_WARPS) {
-                    const int nrows = (int)min((int64_t)DA_WARPS, seg_end - r0);
+                for (int64_t r0 = r; r0 < seg_end; r0 += NW) {
+                    const int nrows = (int)min((int64_t)NW, seg_end - r0);
                     da_mbar_wait(da_smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t bytes = (uint32_t)nrows * row_elems * sizeof(T);
                     const uint32_t fb = da_smem_u32(&full_bar[stage]);
@@ -352,8 +355,8 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                 for (int e = 0; e < 8; ++e) qf[s][e] = to_f32(qb[slot * 8 + e]);
             }
         }
-        for (int64_t r0 = r; r0 < seg_end; r0 += DA_WARPS) {
-            const int nrows = (int)min((int64_t)DA_WARPS, seg_end - r0);
+        for (int64_t r0 = r; r0 < seg_end; r0 += NW) {
+            const int nrows = (int)min((int64_t)NW, seg_end - r0);
             da_mbar_wait(da_smem_u32(&full_bar[stage]), phase);
             if (warp < nrows) {
                 const T* row = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)stage * stage_bytes) +
@@ -393,8 +396,8 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
         // 4-record buffer (warps 4-7 -> 0-3, 2-3 -> 0-1, 1 -> 0): half the shared memory of an 8-record buffer,
         // which is what lets a decode-step GEMM CTA of the other sub-batch share the SM (model.cu, split decode).
 #pragma unroll
-        for (int half = DA_WARPS / 2; half >= 1; half >>= 1) {
-            if (warp >= half && warp < 2 * half) {
+        for (int half = 4; half >= 1; half >>= 1) {
+            if (warp >= half && warp < 2 * half && warp < NW) {
 #pragma unroll
                 for (int s = 0; s < DA_MAXSLOT; ++s) {
                     const int slot = lane + 32 * s;
@@ -407,8 +410,8 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                     }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
-            if (warp < half) {
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            if (warp < half && warp + half < NW) {
 #pragma unroll
                 for (int s = 0; s < DA_MAXSLOT; ++s) {
                     const int slot = lane + 32 * s;
@@ -426,7 +429,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                     }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(DA_WARPS * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
         }
         if (warp == 0) {
             float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
@@ -611,27 +614,34 @@ template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                       float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, bool stream_pdl) {
     (void)decode_attention_partial_floats(B, H);
-    // split decode: 3 stages (144 KB with the merge buffer) leave room for a decode-step GEMM CTA on the same SM
+    // split decode ("lite"): 7 consumer warps and 3 stages (129 KB with the merge buffer, two warps per SM sub-partition) leave
+    // room for a decode-step GEMM CTA of another sub-batch on the same SM
+    const bool lite = g_decode_lite;
     static const int env_stages = getenv("TWB200_DA_STAGES") ? atoi(getenv("TWB200_DA_STAGES")) : 0;      // tuning knob
-    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, g_decode_lite ? 3 : (env_stages >= 2 ? env_stages : DA_MAX_STAGES));
+    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, lite ? 3 : (env_stages >= 2 ? env_stages : DA_MAX_STAGES), lite ? 7 : 8);
     if (d_tk) p.G = g_da_sm_count;               // row count only known on the device: launch every CTA
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
-        cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(decode_attention_stream<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(decode_attention_stream<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         // keep the SM's shared-memory carveout at its maximum so that CTAs of other decode-step kernels fit next to this one
         if (!(getenv("TWB200_CARVEOUT") && atoi(getenv("TWB200_CARVEOUT")) == 0))
-            cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(decode_attention_stream<T, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set[which] = true;
     }
     if (ev0) cudaEventRecord(ev0, st);
     const int kv_static = d_tk ? 0 : 1;
-    // stream_pdl = false (split decode): as a programmatic dependent the CTAs would become resident — 144 KB of shared
+    // stream_pdl = false (split decode): as a programmatic dependent the CTAs would become resident — 129 KB of shared
     // memory each — while their predecessor still runs, and keep the other sub-batch's streaming CTAs off the SMs
     const bool pdl_saved = g_pdl;
     if (!stream_pdl) g_pdl = false;
-    launch_k(decode_attention_stream<T>, dim3(p.G), dim3(DA_THREADS), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
-             p.stages, kv_static, partial);
+    if (lite)
+        launch_k(decode_attention_stream<T, 7>, dim3(p.G), dim3(8 * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
+                 p.stages, kv_static, partial);
+    else
+        launch_k(decode_attention_stream<T, 8>, dim3(p.G), dim3(9 * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
+                 p.stages, kv_static, partial);
     g_pdl = pdl_saved;
     if (ev1) cudaEventRecord(ev1, st);
     launch_k(decode_attention_combine<T>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);

@@ -1,0 +1,57 @@
+"""CPU: host logic of the first-pass transcription pipeline — segment assembly from timestamp tokens and
+the CSV wire format of ref pseudo-labelling/initial_inference.py:47-54 as read by ref pseudo-labelling/prepare_dataset.py:37-53."""
+import csv
+
+import pytest
+
+from taiwan_whisper_b200.configs import token_ids
+from taiwan_whisper_b200.pipeline import Segment, save_transcription_to_csv, segments_from_tokens
+
+IDS = token_ids(51866)
+TSB, EOS = IDS.timestamp_begin, IDS.eos
+
+
+def ts(sec):
+    return TSB + int(round(sec / 0.02))
+
+
+def test_segments_pairs_and_offsets():
+    toks = [ts(0.0), 11, 12, ts(2.5), ts(2.5), 13, ts(4.0), IDS.eos, IDS.eos]
+    seg = segments_from_tokens(toks, TSB, EOS, window_start_s=30.0, window_len_s=30.0)
+    assert seg == [(30.0, 32.5, [11, 12]), (32.5, 34.0, [13])]
+
+
+def test_segment_without_closing_timestamp_runs_to_window_end():
+    seg = segments_from_tokens([ts(1.0), 5, 6, 7], TSB, EOS, 0.0, 12.0)
+    assert seg == [(1.0, 12.0, [5, 6, 7])]
+    # text before any timestamp starts at the window start; timestamps past the window are clipped to its length
+    seg = segments_from_tokens([5, ts(29.0)], TSB, EOS, 60.0, 10.0)
+    assert seg == [(60.0, 70.0, [5])]
+
+
+def test_special_tokens_and_empty_windows():
+    assert segments_from_tokens([], TSB, EOS, 0.0, 30.0) == []
+    assert segments_from_tokens([ts(0.0), ts(0.0), EOS], TSB, EOS, 0.0, 30.0) == []
+    seg = segments_from_tokens([ts(0.0), IDS.sot, 9, IDS.notimestamps, ts(1.0)], TSB, EOS, 0.0, 30.0)
+    assert seg == [(0.0, 1.0, [9])]
+
+
+def test_csv_wire_format(tmp_path):
+    p = tmp_path / "a.csv"
+    save_transcription_to_csv([Segment(0.251, 18.909, "你好, world", [1]), {"start": "19.00", "end": "20.50", "text": "x"}], str(p))
+    lines = p.read_text(encoding="utf-8").splitlines()
+    assert lines[0] == "start,end,text" and lines[1] == '0.25,18.91,"你好, world"'
+    # the reference's reader (prepare_dataset.py:37-53): csv.reader, skip header, 3 fields, float(start), float(end), text.strip()
+    with open(p, "r", encoding="utf-8") as f:
+        r = csv.reader(f)
+        next(r)
+        rows = [(float(a), float(b), c.strip()) for a, b, c in r]
+    assert rows == [(0.25, 18.91, "你好, world"), (19.0, 20.5, "x")]
+
+
+def test_pipeline_argument_errors():
+    from taiwan_whisper_b200.pipeline import B200BatchedInferencePipeline
+    with pytest.raises(NotImplementedError):
+        B200BatchedInferencePipeline(model=None, use_vad_model=True)
+    with pytest.raises(ValueError):
+        B200BatchedInferencePipeline(model=None, chunk_length=45)
