@@ -254,7 +254,7 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
     p.G = g;
     p.R = ceil_div(total_rows, g);
     const size_t stage_bytes = (size_t)nw * 2 * H * HD * esz;
-    const size_t merge_bytes = (size_t)((nw + 1) / 2) * H * DA_PSTRIDE * sizeof(float);
+    const size_t merge_bytes = (size_t)(nw == 8 ? 8 : 4) * H * DA_PSTRIDE * sizeof(float);
     int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
     if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
     if (st > max_stages) st = max_stages;
@@ -278,7 +278,7 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     const uint32_t stage_bytes = (uint32_t)NW * row_elems * sizeof(T);
     T* ring = reinterpret_cast<T*>(da_raw);
     float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(((NW + 1) / 2)) * H * DA_PSTRIDE * sizeof(float));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(NW == 8 ? 8 : 4) * H * DA_PSTRIDE * sizeof(float));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
@@ -392,56 +392,93 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
             if (lane == 0) da_mbar_arrive(da_smem_u32(&empty_bar[stage]));
             if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        // ---- merge the 8 warps of this clip segment -> one partial record per head.  Tree merge through a
-        // 4-record buffer (warps 4-7 -> 0-3, 2-3 -> 0-1, 1 -> 0): half the shared memory of an 8-record buffer,
-        // which is what lets a decode-step GEMM CTA of the other sub-batch share the SM (model.cu, split decode).
-#pragma unroll
-        for (int half = 4; half >= 1; half >>= 1) {
-            if (warp >= half && warp < 2 * half && warp < NW) {
-#pragma unroll
-                for (int s = 0; s < DA_MAXSLOT; ++s) {
-                    const int slot = lane + 32 * s;
-                    if (slot < nslots) {
-                        const int h = slot >> 3, e0 = (slot & 7) * 8;
-                        float* rec = merge + ((size_t)(warp - half) * H + h) * DA_PSTRIDE;
-                        if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            if (warp < half && warp + half < NW) {
-#pragma unroll
-                for (int s = 0; s < DA_MAXSLOT; ++s) {
-                    const int slot = lane + 32 * s;
-                    if (slot < nslots) {
-                        const int h = slot >> 3, e0 = (slot & 7) * 8;
-                        const float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
-                        const float m2 = rec[0], l2 = rec[1];
-                        const float m_new = fmaxf(mrun[s], m2);
-                        const float sc1 = (mrun[s] == -INFINITY) ? 0.0f : __expf(mrun[s] - m_new);
-                        const float sc2 = (m2 == -INFINITY) ? 0.0f : __expf(m2 - m_new);
-                        lrun[s] = lrun[s] * sc1 + l2 * sc2;
-                        mrun[s] = m_new;
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) of[s][e] = of[s][e] * sc1 + rec[2 + e0 + e] * sc2;
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-        }
-        if (warp == 0) {
-            float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
-#pragma unroll
+        if constexpr (NW == 8) {
+            // unsplit decode: all 8 warps post their records, then 256 threads reduce them in parallel (shortest tail;
+            // the tree merge below costs ~2 us more per launch in situ)
+            // ---- merge the 8 warps of this clip segment -> one partial record per head
+    #pragma unroll
             for (int s = 0; s < DA_MAXSLOT; ++s) {
                 const int slot = lane + 32 * s;
                 if (slot < nslots) {
                     const int h = slot >> 3, e0 = (slot & 7) * 8;
-                    float* prec = prec_base + (size_t)h * DA_PSTRIDE;
-                    if ((slot & 7) == 0) { prec[0] = mrun[s]; prec[1] = lrun[s]; }
-#pragma unroll
-                    for (int e = 0; e < 8; e += 2) *reinterpret_cast<float2*>(prec + 2 + e0 + e) = make_float2(of[s][e], of[s][e + 1]);
+                    float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
+                    if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
+    #pragma unroll
+                    for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
+            for (int i = threadIdx.x; i < H * HD; i += NW * 32) {
+                const int h = i / HD, e = i % HD;
+                float m = -INFINITY;
+    #pragma unroll
+                for (int w = 0; w < NW; ++w) m = fmaxf(m, merge[((size_t)w * H + h) * DA_PSTRIDE]);
+                float l = 0.0f, o = 0.0f;
+    #pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const float* rec = merge + ((size_t)w * H + h) * DA_PSTRIDE;
+                    const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
+                    l += rec[1] * sc;
+                    o += rec[2 + e] * sc;
+                }
+                float* prec = prec_base + (size_t)h * DA_PSTRIDE;
+                if (e == 0) { prec[0] = m; prec[1] = l; }
+                prec[2 + e] = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+        } else {
+            // ---- merge the 8 warps of this clip segment -> one partial record per head.  Tree merge through a
+            // 4-record buffer (warps 4-7 -> 0-3, 2-3 -> 0-1, 1 -> 0): half the shared memory of an 8-record buffer,
+            // which is what lets a decode-step GEMM CTA of the other sub-batch share the SM (model.cu, split decode).
+    #pragma unroll
+            for (int half = 4; half >= 1; half >>= 1) {
+                if (warp >= half && warp < 2 * half && warp < NW) {
+    #pragma unroll
+                    for (int s = 0; s < DA_MAXSLOT; ++s) {
+                        const int slot = lane + 32 * s;
+                        if (slot < nslots) {
+                            const int h = slot >> 3, e0 = (slot & 7) * 8;
+                            float* rec = merge + ((size_t)(warp - half) * H + h) * DA_PSTRIDE;
+                            if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
+    #pragma unroll
+                            for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+                if (warp < half && warp + half < NW) {
+    #pragma unroll
+                    for (int s = 0; s < DA_MAXSLOT; ++s) {
+                        const int slot = lane + 32 * s;
+                        if (slot < nslots) {
+                            const int h = slot >> 3, e0 = (slot & 7) * 8;
+                            const float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
+                            const float m2 = rec[0], l2 = rec[1];
+                            const float m_new = fmaxf(mrun[s], m2);
+                            const float sc1 = (mrun[s] == -INFINITY) ? 0.0f : __expf(mrun[s] - m_new);
+                            const float sc2 = (m2 == -INFINITY) ? 0.0f : __expf(m2 - m_new);
+                            lrun[s] = lrun[s] * sc1 + l2 * sc2;
+                            mrun[s] = m_new;
+    #pragma unroll
+                            for (int e = 0; e < 8; ++e) of[s][e] = of[s][e] * sc1 + rec[2 + e0 + e] * sc2;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+            }
+            if (warp == 0) {
+                float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
+    #pragma unroll
+                for (int s = 0; s < DA_MAXSLOT; ++s) {
+                    const int slot = lane + 32 * s;
+                    if (slot < nslots) {
+                        const int h = slot >> 3, e0 = (slot & 7) * 8;
+                        float* prec = prec_base + (size_t)h * DA_PSTRIDE;
+                        if ((slot & 7) == 0) { prec[0] = mrun[s]; prec[1] = lrun[s]; }
+    #pragma unroll
+                        for (int e = 0; e < 8; e += 2) *reinterpret_cast<float2*>(prec + 2 + e0 + e) = make_float2(of[s][e], of[s][e + 1]);
+                    }
                 }
             }
         }
@@ -502,7 +539,7 @@ template <> struct Ld8<__nv_bfloat16> {
 // SA_UNR = rows in flight per warp.  The <T, 2> variant is capped at 64 registers so that a CTA fits next to a resident
 // cross-attention streaming CTA of the other sub-batch (split decode, model.cu).
 template <typename T, int SA_UNR>
-__global__ void __launch_bounds__(SA_WARPS * 32, SA_UNR == 2 ? 4 : 1)
+__global__ void __launch_bounds__(SA_WARPS * 32, SA_UNR == 2 ? 4 : (sizeof(T) == 2 ? 3 : 1))   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
