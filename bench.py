@@ -230,7 +230,7 @@ def main():
         hf = build_hf_model(sh, seed=1234)
     model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev))
     hf_cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is reported at N=1 only
         hf_cpu = hf.to("cpu")
     del hf
     torch.cuda.empty_cache()
