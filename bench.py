@@ -141,6 +141,12 @@ def run_reference(args, rank, world):
     threads) on a bounded sample of the workload: each step = 1 clip of the batch, full token budget."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; once torch has started its OpenMP pool under that setting,
+    # torch.set_num_threads() no longer widens it (measured: 10x slower matmul).  This arm is the reference on ALL host
+    # cores, and only rank 0 works, so lift the cap before torch is imported.
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        if os.environ.get(var) == "1":
+            os.environ[var] = str(os.cpu_count() or 1)
     import numpy as np
     import torch
     from oracle import hf_ref
