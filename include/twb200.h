@@ -166,6 +166,12 @@ TW_API int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, d
 TW_API int tw_decoder_logits(tw_model* m, const void* enc_out, int B, const int32_t* decoder_input_ids, int T, float* logits,
                              int64_t ld_logits, void* stream);
 
+/* Test / profiling entry point: decoder self-attention over the PAGED K|V cache.  pool: [n_pages][16][2*64*H] (a page holds
+ * 16 positions, row = K(d) then V(d)); page_table: device int32 [B][pt_stride], physical page of each clip's logical page;
+ * Tk rows per clip.  The model keeps one such pool per decoder layer and rewrites the table for every decode call. */
+TW_API int tw_debug_self_attention_paged(tw_ctx* ctx, const void* q, int64_t q_stride, const void* pool, const int32_t* page_table,
+                                         int pt_stride, int Tk, int B, int H, int dtype, void* out, void* stream);
+
 /* Test / profiling entry point: attention of the full-sequence decoder pass.  Sq query rows per clip in q (row pitch q_ld
  * elements, head h at column q_col0 + 64 h) against Sk key / value rows per clip in kv (pitch kv_ld, K at k_col0 + 64 h, V at
  * v_col0 + 64 h); causal != 0 masks keys later than the query (needs Sq == Sk).  out [B*Sq, 64 H].  impl 1 = tcgen05 kernel

@@ -514,6 +514,7 @@ decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_
 // warps merged through shared memory, normalised output written directly (single launch, no partial records).
 constexpr int SA_HG = 4;            // heads per CTA: 4 x 64 dims = 32 lanes x 8 elements
 constexpr int SA_WARPS = 8;
+constexpr int SA_MAX_PAGES = 64;     // page-table entries of one clip staged in shared memory (Whisper: 448 / 16 = 28)
 
 template <typename T> struct Ld8;
 template <> struct Ld8<float> {
@@ -541,17 +542,30 @@ template <> struct Ld8<__nv_bfloat16> {
 template <typename T, int SA_UNR>
 __global__ void __launch_bounds__(SA_WARPS * 32, SA_UNR == 2 ? 4 : (sizeof(T) == 2 ? 3 : 1))   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
-                             const int32_t* __restrict__ d_tk, int H, T* __restrict__ out) {
+                             const int32_t* __restrict__ d_tk, int H, T* __restrict__ out, const int32_t* __restrict__ page_table,
+                             int pt_stride) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
+    __shared__ int32_t s_pt[SA_MAX_PAGES];
     pdl_trigger();
-    pdl_wait();                                      // q and the newest cache row come from the QKV GEMM just before
     const int hg = blockIdx.x, b = blockIdx.y;
+    // the page table is fixed for the whole decode call: stage this clip's row in shared memory before the dependency wait,
+    // so that the per-row page lookup is not a dependent global load in front of every K|V row fetch
+    const bool pt_smem = page_table && pt_stride <= SA_MAX_PAGES;
+    if (pt_smem && (int)threadIdx.x < pt_stride) s_pt[threadIdx.x] = page_table[(int64_t)b * pt_stride + threadIdx.x];
+    pdl_wait();                                      // q and the newest cache row come from the QKV GEMM just before
+    if (pt_smem) __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (d_tk) Tk = *d_tk + 1;
     const int d = H * HD;
     const int col = hg * SA_HG * HD + lane * 8;       // this lane's 8 dims inside the row
     const bool active = col < d;
-    const T* kvb = kv + (int64_t)b * kv_clip_stride + (active ? col : 0);
+    // contiguous cache: row r of clip b at kv + b*kv_clip_stride + r*2d; paged cache: pool row kv_page_row(table, ., b, r)
+    const T* kvb = kv + (page_table ? 0 : (int64_t)b * kv_clip_stride) + (active ? col : 0);
+    const int32_t* ptb = page_table ? (pt_smem ? s_pt : page_table + (int64_t)b * pt_stride) : nullptr;
+    auto row_ptr = [&](int r) -> const T* {
+        const int64_t pr = ptb ? (int64_t)ptb[r / TW_KV_PAGE] * TW_KV_PAGE + r % TW_KV_PAGE : (int64_t)r;
+        return kvb + pr * 2 * d;
+    };
     float qf[8], of[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { qf[e] = 0.0f; of[e] = 0.0f; }
@@ -566,8 +580,9 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
         for (int u = 0; u < SA_UNR; ++u) {
             const int r = r0 + u * SA_WARPS;
             if (r < Tk && active) {
-                kr[u] = Ld8<T>::load(kvb + (int64_t)r * 2 * d);
-                vr[u] = Ld8<T>::load(kvb + (int64_t)r * 2 * d + d);
+                const T* rp = row_ptr(r);
+                kr[u] = Ld8<T>::load(rp);
+                vr[u] = Ld8<T>::load(rp + d);
             }
         }
 #pragma unroll
@@ -624,17 +639,19 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
 
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                           T* out, cudaStream_t st) {
+                           T* out, cudaStream_t st, const int32_t* page_table, int pt_stride) {
     dim3 grid(ceil_div(H, SA_HG), B);
     if (g_decode_lite && sizeof(T) == 2)
-        launch_k(self_attention_decode_kernel<T, 2>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+        launch_k(self_attention_decode_kernel<T, 2>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
+                 page_table, pt_stride);
     else
-        launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out);
+        launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
+                 page_table, pt_stride);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
-                                           cudaStream_t);
+                                           cudaStream_t, const int32_t*, int);
 template void self_attention_decode<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*,
-                                                   int, int, __nv_bfloat16*, cudaStream_t);
+                                                   int, int, __nv_bfloat16*, cudaStream_t, const int32_t*, int);
 
 static int g_da_sm_count = 0;
 size_t decode_attention_partial_floats(int B, int H) {

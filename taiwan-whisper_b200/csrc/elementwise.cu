@@ -240,21 +240,23 @@ template void embed_tokens_seq<__nv_bfloat16>(const int32_t*, const __nv_bfloat1
 // ---- self-attention KV cache append: cache[b][pos][0:2d] = qkv[b][d:3d]
 template <typename T>
 __global__ void kv_append_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ d_step, int d,
-                                 int max_len) {
+                                 int max_len, const int32_t* __restrict__ page_table, int pt_stride) {
     pdl_trigger();
     pdl_wait();
     const int b = blockIdx.x;
     const int pos = d_step[0];
     const T* src = qkv + (int64_t)b * 3 * d + d;
-    T* dst = cache + ((int64_t)b * max_len + pos) * 2 * d;
+    T* dst = cache + (page_table ? kv_page_row(page_table, pt_stride, b, pos) : (int64_t)b * max_len + pos) * 2 * d;
     for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) dst[i] = src[i];
 }
 template <typename T>
-void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st) {
-    launch_k(kv_append_kernel<T>, dim3(B), dim3(256), 0, st, qkv, cache, d_step, d, max_len);
+void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st, const int32_t* page_table,
+               int pt_stride) {
+    launch_k(kv_append_kernel<T>, dim3(B), dim3(256), 0, st, qkv, cache, d_step, d, max_len, page_table, pt_stride);
 }
-template void kv_append<float>(const float*, float*, const int32_t*, int, int, int, cudaStream_t);
-template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const int32_t*, int, int, int, cudaStream_t);
+template void kv_append<float>(const float*, float*, const int32_t*, int, int, int, cudaStream_t, const int32_t*, int);
+template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const int32_t*, int, int, int, cudaStream_t, const int32_t*,
+                                       int);
 
 __global__ void advance_step_kernel(int32_t* d_step) {
     pdl_trigger();

@@ -167,8 +167,9 @@ gemm_skinny_kernel(SkinnyArgs a) {
             if (e.mode == EPI_GELU) v = gelu_erf(v);
             if (n < e.n_split) reinterpret_cast<__nv_bfloat16*>(e.C)[(int64_t)m * e.ldc + n] = __float2bfloat16_rn(v);
             else
-                reinterpret_cast<__nv_bfloat16*>(e.C2)[(int64_t)m * e.ldc2 + (n - e.n_split) +
-                                                       (e.d_row2 ? (int64_t)(*e.d_row2) * e.row2_stride : 0)] = __float2bfloat16_rn(v);
+                reinterpret_cast<__nv_bfloat16*>(e.C2)[(n - e.n_split) +
+                    (e.page_table ? kv_page_row(e.page_table, e.pt_stride, m, *e.d_row2) * e.row2_stride
+                                  : (int64_t)m * e.ldc2 + (e.d_row2 ? (int64_t)(*e.d_row2) * e.row2_stride : 0))] = __float2bfloat16_rn(v);
         } else if (e.mode == EPI_RESID) {
             float* dst = reinterpret_cast<float*>(e.C) + (int64_t)m * e.ldc + n;
             if (split) atomicAdd(dst, v);

@@ -320,8 +320,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(epi.C) + o;
                     if (n0 >= epi.n_split)       // column split (fused QKV: K|V go straight into the cache row of this position)
-                        cp = reinterpret_cast<__nv_bfloat16*>(epi.C2) + (int64_t)row * epi.ldc2 + (n0 - epi.n_split) +
-                             (epi.d_row2 ? (int64_t)(*epi.d_row2) * epi.row2_stride : 0);
+                        cp = reinterpret_cast<__nv_bfloat16*>(epi.C2) + (n0 - epi.n_split) +
+                                 (epi.page_table ? kv_page_row(epi.page_table, epi.pt_stride, row, *epi.d_row2) * epi.row2_stride
+                                                 : (int64_t)row * epi.ldc2 + (epi.d_row2 ? (int64_t)(*epi.d_row2) * epi.row2_stride : 0));
                     if (full && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {

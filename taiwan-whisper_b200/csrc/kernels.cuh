@@ -33,6 +33,10 @@ struct GemmEpi {
     int64_t ldc2 = 0;
     const int32_t* d_row2 = nullptr;   // device int: extra row offset (*d_row2 * row2_stride elements) into C2 — the cache position
     int64_t row2_stride = 0;
+    // paged self-attention cache: when page_table is given, output row m at position pos = *d_row2 lands in pool row
+    // kv_page_row(page_table, pt_stride, m, pos) of C2 (row pitch row2_stride) instead of m*ldc2 + pos*row2_stride
+    const int32_t* page_table = nullptr;
+    int pt_stride = 0;
 };
 
 // CUDA-core FMA GEMM, fp32 accumulate in a fixed order; the fp32 check-mode path (T = float)
@@ -57,6 +61,13 @@ bool gemm_skinny_supported(int M, int N, int K, const GemmEpi& epi);
 int gemm_skinny(tw_ctx* ctx, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
                 const GemmEpi& epi, cudaStream_t st);
 
+// ---- paged self-attention K|V cache: TW_KV_PAGE positions per page; page_table[clip * pt_stride + pos / TW_KV_PAGE] is the
+// physical page of a clip's logical page inside the layer's pool [n_pages][TW_KV_PAGE][2d]
+constexpr int TW_KV_PAGE = 16;
+__host__ __device__ __forceinline__ int64_t kv_page_row(const int32_t* page_table, int pt_stride, int clip, int pos) {
+    return (int64_t)page_table[(int64_t)clip * pt_stride + pos / TW_KV_PAGE] * TW_KV_PAGE + pos % TW_KV_PAGE;
+}
+
 // ---- elementwise / normalisation (elementwise.cu)
 template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int M, int d, cudaStream_t st);
@@ -76,9 +87,10 @@ void embed_tokens(const int32_t* tok, const T* E, const T* P, const int32_t* d_s
 // full token sequences: x[b*T + t] = E[tok[b*T + t]] + P[t]
 template <typename T>
 void embed_tokens_seq(const int32_t* tok, const T* E, const T* P, float* x, int B, int Tn, int d, int vocab, cudaStream_t st);
-// cache[b][pos][0:2d] = qkv[b][d:3d]
+// cache[b][pos][0:2d] = qkv[b][d:3d]   (with a page table: pool row kv_page_row(table, pt_stride, b, pos))
 template <typename T>
-void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st);
+void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st,
+               const int32_t* page_table = nullptr, int pt_stride = 0);
 void advance_step(int32_t* d_step, cudaStream_t st);
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 
@@ -108,7 +120,7 @@ size_t decode_attention_partial_floats(int B, int H);
 // single-launch self-attention over the short decoder cache (Tk = *d_tk + 1 when d_tk is given)
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                           T* out, cudaStream_t st);   // size of the partial workspace
+                           T* out, cudaStream_t st, const int32_t* page_table = nullptr, int pt_stride = 0);   // size of the partial workspace
 
 // ---- token selection (select.cu)
 struct RulesDev {

@@ -119,7 +119,12 @@ struct tw_model {
          *ws_enc = nullptr;
     float* ws_x = nullptr;
     void* xkv = nullptr;       // [L_dec][maxB*1500][2d]
-    void* self_kv = nullptr;   // [L_dec][maxB][max_target][2d]
+    // paged self-attention K|V cache: per decoder layer a pool [max_batch * kv_pages][TW_KV_PAGE][2d]; one page table
+    // [max_batch][kv_pages] (physical page of each clip's logical page) shared by all layers, rewritten per decode call
+    void* self_kv = nullptr;
+    int kv_pages = 0;                  // logical pages per clip = ceil(max_target / TW_KV_PAGE)
+    int32_t* d_page_table = nullptr;
+    int32_t* h_page_table = nullptr;   // pinned staging
     float *dx = nullptr, *dlogits = nullptr, *dpartial = nullptr;
     void *dxn = nullptr, *dqkv = nullptr, *datt = nullptr, *dq = nullptr, *dhmid = nullptr;
     int32_t* dstate = nullptr;  // 6*maxB + 1 ints
@@ -324,7 +329,10 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, &m->ws_hmid, M * D.ffn * e));
     TW_CHECK(dev_alloc(m, &m->ws_enc, M * d * e));
     TW_CHECK(dev_alloc(m, &m->xkv, (size_t)D.dec_layers * M * 2 * d * e));
-    TW_CHECK(dev_alloc(m, &m->self_kv, (size_t)D.dec_layers * B * D.max_target * 2 * d * e));
+    m->kv_pages = (D.max_target + TW_KV_PAGE - 1) / TW_KV_PAGE;
+    TW_CHECK(dev_alloc(m, &m->self_kv, (size_t)D.dec_layers * B * m->kv_pages * TW_KV_PAGE * 2 * d * e));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_page_table, B * m->kv_pages * sizeof(int32_t)));
+    TW_CUDA_OK(m->ctx, cudaMallocHost(&m->h_page_table, B * m->kv_pages * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->dx, B * d * sizeof(float)));
     TW_CHECK(dev_alloc(m, &m->dxn, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dqkv, B * 3 * d * e));
@@ -555,7 +563,7 @@ int launch_step(tw_model* m, int B, int nsplit, const RulesDev& R, const DecodeS
     const int d = D.d_model, V = D.vocab, H = D.heads;
     float* x = m->dx;
     T* xn = (T*)m->dxn; T* qkv = (T*)m->dqkv; T* att = (T*)m->datt; T* q = (T*)m->dq; T* hmid = (T*)m->dhmid;
-    const size_t self_layer = (size_t)D.max_batch * D.max_target * 2 * d;
+    const size_t self_layer = (size_t)D.max_batch * m->kv_pages * TW_KV_PAGE * 2 * d;      // one layer's page pool
     const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
     const int32_t* d_pos = m->d_step + STEP_POS;
     // PDL only on the bf16 product path: every kernel launched below goes through launch_k and executes pdl_wait()
@@ -594,7 +602,8 @@ int launch_step(tw_model* m, int B, int nsplit, const RulesDev& R, const DecodeS
             float* xh = x + (size_t)b0 * d;
             T* xnh = xn + (size_t)b0 * d; T* qkvh = qkv + (size_t)b0 * 3 * d; T* atth = att + (size_t)b0 * d;
             T* qh = q + (size_t)b0 * d; T* hmidh = hmid + (size_t)b0 * D.ffn;
-            T* cache = (T*)m->self_kv + l * self_layer + (size_t)b0 * D.max_target * 2 * d;
+            T* cache = (T*)m->self_kv + l * self_layer;                       // the layer's page pool
+            const int32_t* pt = m->d_page_table + (size_t)b0 * m->kv_pages;   // page table rows of this sub-batch
             // the first kernel after the fork depends on another stream's work: a full (not programmatic) dependency
             if (nsplit > 1 && l == 0) g_pdl = false;
             layernorm<T>(xh, L.ln1_g, L.ln1_b, xnh, Bh, d, ss);
@@ -605,14 +614,16 @@ int launch_step(tw_model* m, int B, int nsplit, const RulesDev& R, const DecodeS
             if (fused_append) {      // the K|V columns of the fused QKV projection land in the cache row of this position
                 qe.n_split = d;
                 qe.C2 = cache;
-                qe.ldc2 = (int64_t)D.max_target * 2 * d;
+                qe.ldc2 = 0;
                 qe.d_row2 = d_pos;
                 qe.row2_stride = 2 * d;
+                qe.page_table = pt;
+                qe.pt_stride = m->kv_pages;
             }
             TW_CHECK(gemm<T>(m, xnh, d, (const T*)L.self.qkv_w, d, Bh, 3 * d, d, qe, ss));
             mark(l, h, "qkv", ss);
-            if (!fused_append) { kv_append<T>(qkvh, cache, m->d_step, Bh, d, D.max_target, ss); ctx->launches += 1; }
-            self_attention_decode<T>(qkvh, 3 * d, cache, (int64_t)D.max_target * 2 * d, 0, d_pos, Bh, H, atth, ss);
+            if (!fused_append) { kv_append<T>(qkvh, cache, m->d_step, Bh, d, D.max_target, ss, pt, m->kv_pages); ctx->launches += 1; }
+            self_attention_decode<T>(qkvh, 3 * d, cache, 0, 0, d_pos, Bh, H, atth, ss, pt, m->kv_pages);
             mark(l, h, "self_attn", ss);
             TW_CHECK(gemm<T>(m, atth, d, (const T*)L.self.o_w, d, Bh, d, d, mk_epi(EPI_RESID, L.self.o_b, xh, d), ss));
             mark(l, h, "self_o", ss);
@@ -697,6 +708,16 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     for (int i = 0; i < P; ++i) hs[STEP_PROMPT + i] = prompt[i];
     TW_CUDA_OK(ctx, cudaMemcpyAsync(m->d_step, hs, STEP_INTS * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     ctx->launches += 1;
+    // page table of this call: only the ceil(max_length / TW_KV_PAGE) pages a clip can reach are mapped, page-major
+    // (logical page p of clip b -> physical page p*B + b), so a call touches a dense prefix of every layer's pool whose
+    // size follows B and max_length, and the B cache rows written by one step are adjacent
+    {
+        const int pages_call = (max_length + TW_KV_PAGE - 1) / TW_KV_PAGE;
+        for (int b = 0; b < B; ++b)
+            for (int p = 0; p < m->kv_pages; ++p) m->h_page_table[b * m->kv_pages + p] = p < pages_call ? p * B + b : -1;
+        TW_CUDA_OK(ctx, cudaMemcpyAsync(m->d_page_table, m->h_page_table, (size_t)B * m->kv_pages * sizeof(int32_t),
+                                        cudaMemcpyHostToDevice, st));
+    }
 
     // CUDA graph of one step: production path only (no teacher forcing / taps / per-launch profiling events)
     const bool want_graph = m->use_graph && !forced && !logits_tap && !m->prof_on && m->trace_pos < 0;
@@ -907,6 +928,7 @@ void tw_model_free(tw_model* m) {
     for (void* p : m->allocs) cudaFree(p);
     if (m->h_flag) cudaFreeHost(m->h_flag);
     if (m->h_step) cudaFreeHost(m->h_step);
+    if (m->h_page_table) cudaFreeHost(m->h_page_table);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
     for (int h = 0; h < TW_MAX_SPLIT; ++h) {
@@ -1111,6 +1133,21 @@ int tw_debug_self_attention(tw_ctx* ctx, const void* q, int64_t q_stride, const 
                                              H, (__nv_bfloat16*)out, st);
     else
         self_attention_decode<float>((const float*)q, q_stride, (const float*)kv, kv_clip_stride, Tk, nullptr, B, H, (float*)out, st);
+    ctx->launches += 1;
+    TW_CUDA_OK(ctx, cudaGetLastError());
+    return TW_OK;
+}
+
+int tw_debug_self_attention_paged(tw_ctx* ctx, const void* q, int64_t q_stride, const void* pool, const int32_t* page_table,
+                                  int pt_stride, int Tk, int B, int H, int dtype, void* out, void* stream) {
+    if (!ctx || !q || !pool || !page_table || !out || B <= 0 || Tk <= 0 || H <= 0 || pt_stride <= 0) return TW_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TW_BF16)
+        self_attention_decode<__nv_bfloat16>((const __nv_bfloat16*)q, q_stride, (const __nv_bfloat16*)pool, 0, Tk, nullptr, B, H,
+                                             (__nv_bfloat16*)out, st, page_table, pt_stride);
+    else
+        self_attention_decode<float>((const float*)q, q_stride, (const float*)pool, 0, Tk, nullptr, B, H, (float*)out, st, page_table,
+                                     pt_stride);
     ctx->launches += 1;
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;

@@ -278,6 +278,40 @@ def test_decode_attention_kernel_vs_torch(Tk, B, H, entry, lite):
     ctx.lib.tw_debug_set_lite(0)
 
 
+@pytest.mark.parametrize("Tk,B,H", [(1, 2, 2), (16, 3, 6), (37, 5, 20), (448, 7, 2)])
+@pytest.mark.parametrize("lite", [0, 1])
+def test_paged_self_attention_vs_torch(Tk, B, H, lite):
+    """Decoder self-attention over the paged K|V cache with an arbitrary (shuffled) page table: 16 positions per page."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    d = H * 64
+    pages_per_clip = (Tk + 15) // 16
+    pt_stride = pages_per_clip + 2                      # table rows are longer than what a clip uses
+    n_pages = B * pages_per_clip + 3
+    g = torch.Generator(device="cuda").manual_seed(Tk * 31 + B + H)
+    perm = torch.randperm(n_pages, device="cuda", generator=g)[:B * pages_per_clip].view(B, pages_per_clip)
+    table = torch.full((B, pt_stride), -1, dtype=torch.int32, device="cuda")
+    table[:, :pages_per_clip] = perm.to(torch.int32)
+    ctx.lib.tw_debug_set_lite(lite)
+    try:
+        for dt, tw_dt, tol in ((torch.float32, twlib.TW_F32, 1e-4), (torch.bfloat16, twlib.TW_BF16, 1e-2)):
+            pool = torch.randn((n_pages, 16, 2 * d), device="cuda", generator=g).to(dt)
+            q = (torch.randn((B, d), device="cuda", generator=g) * 0.3).to(dt)
+            out = torch.zeros((B, d), device="cuda", dtype=dt)
+            ctx.check(ctx.lib.tw_debug_self_attention_paged(ctx.handle, q.data_ptr(), d, pool.data_ptr(), table.data_ptr(), pt_stride, Tk, B,
+                                                            H, tw_dt, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            kv = pool[perm.reshape(-1)].view(B, pages_per_clip * 16, 2 * d)[:, :Tk]          # gather each clip's logical rows
+            x = kv.float().view(B, Tk, 2, H, 64)
+            sc = torch.einsum("bhd,bthd->bht", q.float().view(B, H, 64), x[:, :, 0])
+            ref = torch.einsum("bht,bthd->bhd", torch.softmax(sc, -1), x[:, :, 1]).reshape(B, d)
+            err = (out.float() - ref).abs().max().item()
+            assert err < tol, (dt, err)
+    finally:
+        ctx.lib.tw_debug_set_lite(0)
+
+
 # ------------------------------------------------------------------------------------------ encoder
 @pytest.mark.parametrize("shape_name", ["tiny", "micro128"])
 def test_encoder_fp32_check_mode(shape_name):
