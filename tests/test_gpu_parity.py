@@ -381,6 +381,23 @@ def test_greedy_tokens_fp32_bit_identical(shape_name, timestamps):
             assert np.abs(tap[s, b][fin] - ref[fin]).max() < 1e-4
 
 
+def test_greedy_tokens_fp32_full_length():
+    """Maximum size: max_length = max_target_positions (448) — every page of the paged self-attention cache and every
+    learned position are used; ids stay bit-identical to the oracle."""
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    sh = SHAPES["tiny"]
+    pcm, mel, ora = oracle_run("tiny", 1, sh.max_target, False)
+    m = b200_model("tiny", "f32")
+    ids = m.generate(torch.from_numpy(mel), max_length=sh.max_target, num_beams=1, return_timestamps=False, language="zh",
+                     task="transcribe").numpy()
+    ref = ora[0]["tokens"]
+    assert len(ref) > 300, len(ref)                       # random-init weights do not emit EOS early
+    assert ids[0, :len(ref)].tolist() == ref
+    with pytest.raises(ValueError):                        # HF: prompt + new tokens must fit max_target_positions
+        m.generate(torch.from_numpy(mel), max_length=sh.max_target + 1, language="zh", task="transcribe")
+
+
 def test_tokens_vs_hf_golden(golden_dir):
     _cuda()
     from tests.gpu_common import b200_model
