@@ -5,8 +5,9 @@ strided view of the recording (row pitch = chunk - stride_left - stride_right sa
 
 Window placement and the (chunk_len, stride_left, stride_right) bookkeeping restate
 ref: training/flax/distil_whisper/pipeline.py:224-254 (chunk_iter_with_batch) and :325-335 (stride = chunk/6).
-Stitching the per-window token streams is tokenizer work (`tokenizer._decode_asr`, ref :353-375) and stays in
-the caller.
+`stitch_windows` merges the per-window token streams of overlapping windows the way `tokenizer._decode_asr` does for
+the no-timestamp case (ref :353-375 -> HF tokenization_whisper.py `_find_longest_common_sequence`); ids -> text stays
+with the tokenizer (third-party vocabulary data).
 """
 from __future__ import annotations
 
@@ -60,3 +61,34 @@ def chunked_log_mel(pcm: torch.Tensor, n_mel: int, chunk_len: int = N_SAMPLES, s
         ctx.check(ctx.lib.tw_logmel(ctx.handle, pcm.data_ptr(), dt, step, n_valid.data_ptr(), n, n_mel, out.data_ptr(),
                                     torch.cuda.current_stream(pcm.device).cuda_stream))
     return out, strides
+
+
+def stitch_windows(sequences: List[List[int]]) -> List[int]:
+    """Merge the token streams of consecutive overlapping windows into one stream (no-timestamp mode).
+
+    Restates HF `_find_longest_common_sequence` (tokenization_whisper.py; called by `_decode_asr`, which
+    ref: training/flax/distil_whisper/pipeline.py:353-375 calls): for each next window slide it over the tail of what
+    has been kept so far; an alignment of overlap length i scores (#equal tokens) / i + i / 10000 (the epsilon prefers
+    longer overlaps) and needs at least two equal tokens; at the best alignment keep the left stream up to the middle of
+    the overlap and continue with the right stream from the middle of its side of the overlap."""
+    if not sequences:
+        return []
+    left = list(sequences[0])
+    total: List[int] = []
+    for right in sequences[1:]:
+        right = list(right)
+        n_l, n_r = len(left), len(right)
+        best, best_idx = 0.0, (n_l, n_l, 0, 0)
+        la, ra = np.asarray(left, dtype=np.int64), np.asarray(right, dtype=np.int64)
+        for i in range(1, n_l + n_r):
+            l0, l1 = max(0, n_l - i), min(n_l, n_l + n_r - i)
+            r0, r1 = max(0, i - n_l), min(n_r, i)
+            matches = int(np.sum(la[l0:l1] == ra[r0:r1]))
+            score = matches / i + i / 10000.0
+            if matches > 1 and score > best:
+                best, best_idx = score, (l0, l1, r0, r1)
+        l0, l1, r0, r1 = best_idx
+        total.extend(left[:(l0 + l1) // 2])
+        left = right[(r0 + r1) // 2:]
+    total.extend(left)
+    return total

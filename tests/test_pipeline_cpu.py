@@ -55,3 +55,27 @@ def test_pipeline_argument_errors():
         B200BatchedInferencePipeline(model=None, use_vad_model=True)
     with pytest.raises(ValueError):
         B200BatchedInferencePipeline(model=None, chunk_length=45)
+
+
+def test_stitch_windows_matches_hf():
+    """Long-form stitching of overlapping windows == HF `_find_longest_common_sequence` (what `tokenizer._decode_asr`, called at
+    ref training/flax/distil_whisper/pipeline.py:353-375, uses in no-timestamp mode), on synthetic overlapping streams with
+    substitution noise in the overlaps."""
+    import numpy as np
+    from transformers.models.whisper.tokenization_whisper import _find_longest_common_sequence
+    from taiwan_whisper_b200.longform import stitch_windows
+    rng = np.random.default_rng(5)
+    for case in range(40):
+        truth = rng.integers(0, 300, size=int(rng.integers(40, 160))).tolist()
+        seqs, pos = [], 0
+        while pos < len(truth):
+            n = int(rng.integers(12, 40))
+            w = truth[pos:pos + n]
+            w = [t if rng.random() > 0.1 else int(rng.integers(0, 300)) for t in w]      # decoding noise
+            seqs.append(w)
+            if pos + n >= len(truth):
+                break
+            pos += n - int(rng.integers(0, 10))                                          # overlap of 0..9 tokens
+        assert stitch_windows(seqs) == _find_longest_common_sequence(seqs), case
+    assert stitch_windows([]) == [] and stitch_windows([[1, 2, 3]]) == [1, 2, 3]
+    assert stitch_windows([[1, 2, 3, 4], [3, 4, 5]]) == [1, 2, 3, 4, 5]
