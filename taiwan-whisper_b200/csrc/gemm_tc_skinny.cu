@@ -346,7 +346,10 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     }
     // lite: set by the split decode (model.cu) — small enough to share an SM with a streaming cross-attention CTA
     const bool lite = g_decode_lite && M <= 32;
-    const int BN = (!lite && ceil_div(N, 32) > ctx->sm_count) ? 64 : 32;
+    // 64-wide tiles once 32-wide ones would need more than `waves` passes over the SMs (tuning knob TWB200_SK_WAVES; 1 = measured default: 2, i.e. fc1 as 160 32-wide
+    // tiles on 148 CTAs instead of 80 64-wide ones, is 12 ms per decode slower)
+    static const int waves = getenv("TWB200_SK_WAVES") ? atoi(getenv("TWB200_SK_WAVES")) : 1;
+    const int BN = (!lite && ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
     CUtensorMap ma, mw;
     TW_CHECK(sk2_map(ctx, A, M, K, lda, lite ? 32 : 64, &ma));
     TW_CHECK(sk2_map(ctx, W, N, K, ldw, BN, &mw));
