@@ -101,6 +101,9 @@ TW_API int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight
 TW_API void tw_model_free(tw_model* m);
 /* bytes of device memory the model holds for weights + workspace at max_batch */
 TW_API size_t tw_model_bytes(const tw_model* m);
+/* Device bytes tw_model_load would allocate for this descriptor (repacked weights, workspace, cross-attention K|V store,
+ * paged self-attention pools) — host arithmetic only, usable for sizing max_batch against the 180 GB of a B200 before loading. */
+TW_API size_t tw_workspace_bytes(const tw_model_desc* desc);
 
 /* WhisperEncoder.forward on B windows: mel float32 [B, n_mel, 3000] (device) ->
  * enc_out [B, 1500, d_model] in the model dtype (device).  tap_layer >= 0 additionally copies the

@@ -944,6 +944,36 @@ void tw_model_free(tw_model* m) {
 
 size_t tw_model_bytes(const tw_model* m) { return m ? m->bytes : 0; }
 
+size_t tw_workspace_bytes(const tw_model_desc* desc) {
+    // Device bytes tw_model_load will allocate for this descriptor (repacked weights + workspace + K|V stores), without
+    // touching a device: the same expressions as load_weights / alloc_workspace (a -m gpu test pins the two together).
+    if (!desc) return 0;
+    const tw_model_desc& D = *desc;
+    if (D.d_model <= 0 || D.ffn <= 0 || D.enc_layers <= 0 || D.dec_layers <= 0 || D.vocab <= 0 || D.max_batch <= 0 || D.max_target <= 0 ||
+        (D.dtype != TW_BF16 && D.dtype != TW_F32))
+        return 0;
+    const size_t e = D.dtype == TW_BF16 ? 2 : 4, f4 = sizeof(float);
+    const size_t d = D.d_model, ffn = D.ffn, V = D.vocab, B = D.max_batch, M = B * TW_N_CTX, dd = d * d;
+    auto al = [](size_t b) { return b == 0 ? (size_t)16 : b; };      // dev_alloc never asks for 0 bytes
+    const size_t ln = 2 * al(d * f4);
+    const size_t attn_self = al(3 * dd * e) + al(3 * d * f4) + al(dd * e) + al(d * f4);
+    const size_t attn_cross = al(dd * e) + al(d * f4) + al(2 * dd * e) + al(2 * d * f4) + al(dd * e) + al(d * f4);
+    const size_t mlp = al(ffn * d * e) + al(ffn * f4) + al(ffn * d * e) + al(d * f4);
+    size_t w = al(d * 3 * D.n_mel * e) + al(d * 3 * d * e) + 2 * al(d * f4) + al((size_t)TW_N_CTX * d * f4);
+    w += (size_t)D.enc_layers * (ln + attn_self + ln + mlp) + ln;
+    w += al(V * d * e) + al((size_t)D.max_target * d * e);
+    w += (size_t)D.dec_layers * (ln + attn_self + ln + attn_cross + ln + mlp) + ln;
+    const size_t kv_pages = (D.max_target + TW_KV_PAGE - 1) / TW_KV_PAGE;
+    size_t ws = al(B * TW_N_SAMPLES * sizeof(int16_t)) + al(B * sizeof(int32_t)) + al(B * D.n_mel * TW_N_FRAMES * f4) +
+                al(B * TW_N_FRAMES * 3 * D.n_mel * e) + al(B * TW_N_FRAMES * d * e) + al(M * 3 * d * e) + al(M * d * f4) +
+                al(M * d * e) + al(M * d * e) + al(M * ffn * e) + al(M * d * e) + al((size_t)D.dec_layers * M * 2 * d * e) +
+                al((size_t)D.dec_layers * B * kv_pages * TW_KV_PAGE * 2 * d * e) + al(B * kv_pages * sizeof(int32_t)) +
+                al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * V * f4) +
+                al(TW_MAX_SPLIT * decode_attention_partial_floats((int)B, D.heads) * f4) + al((6 * B + 4) * sizeof(int32_t)) + al(V) + al(V) +
+                al(4096 * sizeof(int32_t)) + al(B * D.max_target * sizeof(int32_t)) + al(B * sizeof(int32_t)) + al(STEP_INTS * sizeof(int32_t));
+    return w + ws;
+}
+
 int tw_encode(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, void* stream) {
     if (!check_model(m, "tw_encode")) return TW_E_INVALID;
     if (B <= 0 || B > m->desc.max_batch || !mel || !enc_out) {

@@ -180,3 +180,21 @@ def test_chunk_plan_matches_reference_chunker():
     assert starts[1] - starts[0] == 320000 and strides[0][1] == 0 and strides[-1][2] == 0
     with pytest.raises(ValueError):
         chunk_plan(1000, 100, 60, 60)
+
+
+def test_workspace_bytes_is_host_arithmetic():
+    """tw_workspace_bytes needs no device: sizes a descriptor before loading."""
+    from taiwan_whisper_b200 import lib as twlib
+    from taiwan_whisper_b200.configs import SHAPES
+    lib = twlib.load_library()
+    sh = SHAPES["large-v3"]
+
+    def nbytes(max_batch, dtype):
+        desc = twlib.ModelDesc(sh.d_model, sh.ffn, sh.heads, sh.enc_layers, sh.dec_layers, sh.n_mel, sh.vocab, sh.max_target, dtype, max_batch)
+        return int(lib.tw_workspace_bytes(desc))
+
+    b64 = nbytes(64, twlib.TW_BF16)
+    assert 25e9 < b64 < 40e9, b64                        # 3.1 GB weights + 15.7 GB cross-K/V + 4.7 GB cache pools + activations
+    assert nbytes(128, twlib.TW_BF16) > b64 > nbytes(32, twlib.TW_BF16)
+    assert nbytes(64, twlib.TW_F32) > 1.9 * b64 - 1e9
+    assert lib.tw_workspace_bytes(None) == 0

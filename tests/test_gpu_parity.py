@@ -699,3 +699,16 @@ def test_first_pass_pipeline(chunk_length):
     assert [(s.start, s.end, s.tokens) for s in segs][:len(ref)] == ref
     for s in segs:
         assert 0.0 <= s.start <= s.end <= len(rec) / 16000 + 1e-6 and s.text == ",".join(map(str, s.tokens))
+
+
+@pytest.mark.parametrize("shape_name,dtype_name", [("tiny", "f32"), ("micro128", "bf16")])
+def test_workspace_bytes_matches_allocation(shape_name, dtype_name):
+    """tw_workspace_bytes (host arithmetic) == what tw_model_load actually allocated."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    from tests.gpu_common import b200_model
+    sh = SHAPES[shape_name]
+    m = b200_model(shape_name, dtype_name)
+    desc = twlib.ModelDesc(sh.d_model, sh.ffn, sh.heads, sh.enc_layers, sh.dec_layers, sh.n_mel, sh.vocab, sh.max_target,
+                           twlib.TW_F32 if dtype_name == "f32" else twlib.TW_BF16, m.max_batch)
+    assert int(m.ctx.lib.tw_workspace_bytes(desc)) == m.device_bytes()
