@@ -61,7 +61,7 @@ def log_mel(pcm: torch.Tensor, n_valid: Optional[torch.Tensor], n_mel: int) -> t
 
 
 def _register_torch_ops():
-    """torch.ops.twb200.{log_mel, encoder_forward, greedy_generate}: thin operator wrappers over the
+    """torch.ops.twb200.{log_mel, encoder_forward, greedy_generate, decoder_logits}: thin operator wrappers over the
     C ABI (CUDA tensors only, current stream)."""
     try:
         from torch.library import custom_op
@@ -94,6 +94,16 @@ def _register_torch_ops():
     @_op_greedy_generate.register_fake
     def _(handle, enc_out, prompt, max_length, timestamps):
         return enc_out.new_empty((enc_out.shape[0], max_length - len(prompt) + 1), dtype=torch.int32)
+
+    @custom_op("twb200::decoder_logits", mutates_args=())
+    def _op_decoder_logits(handle: int, enc_out: torch.Tensor, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+        # the custom-op contract wants an owning tensor: copy the pitched view into a dense [B, T, V]
+        return _MODELS[handle].decoder_logits(enc_out, decoder_input_ids).contiguous()
+
+    @_op_decoder_logits.register_fake
+    def _(handle, enc_out, decoder_input_ids):
+        m = _MODELS[handle]
+        return enc_out.new_empty((decoder_input_ids.shape[0], decoder_input_ids.shape[1], m.shape.vocab), dtype=torch.float32)
 
 
 _MODELS: dict = {}

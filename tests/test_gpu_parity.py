@@ -665,6 +665,18 @@ def test_torch_ops_registered():
     x = torch.from_numpy(synth_batch(0, 1)).cuda()
     out = torch.ops.twb200.log_mel(x, 80)
     assert out.shape == (1, 80, 3000)
+    # model-level ops go through the handle registry: encoder -> greedy ids / teacher logits
+    from tests.gpu_common import b200_model
+    m = b200_model("tiny", "f32")
+    enc = torch.ops.twb200.encoder_forward(m._id, out)
+    assert torch.equal(enc, m.encode(out))
+    P = prompt_ids(SHAPES["tiny"].vocab, False)
+    packed = torch.ops.twb200.greedy_generate(m._id, enc, P, 16, False)
+    toks, lens = m.decode(enc, P, 16, False)
+    assert torch.equal(packed[:, :-1], toks) and torch.equal(packed[:, -1], lens)
+    ids = torch.tensor([P + [11, 12, 13]], device="cuda")
+    lg = torch.ops.twb200.decoder_logits(m._id, enc, ids)
+    assert lg.shape == (1, 7, SHAPES["tiny"].vocab) and lg.is_contiguous() and torch.equal(lg, m.decoder_logits(enc, ids))
 
 
 @pytest.mark.parametrize("chunk_length", [30, 7])
