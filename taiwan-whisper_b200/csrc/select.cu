@@ -64,7 +64,6 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
                      float* __restrict__ logits_tap) {
     __shared__ Best s_text[32], s_ts[32];
     __shared__ float s_m[32], s_s[32];
-    __shared__ int s_tok;
     __shared__ int s_dom;
     pdl_trigger();
     pdl_wait();
@@ -167,7 +166,6 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
                 nxt = R.pad;
             }
             S.cur_tok[b] = nxt;
-            s_tok = tok;
             s_dom = dominate ? 1 : 0;
         }
     }
