@@ -79,3 +79,26 @@ def test_stitch_windows_matches_hf():
         assert stitch_windows(seqs) == _find_longest_common_sequence(seqs), case
     assert stitch_windows([]) == [] and stitch_windows([[1, 2, 3]]) == [1, 2, 3]
     assert stitch_windows([[1, 2, 3, 4], [3, 4, 5]]) == [1, 2, 3, 4, 5]
+
+
+def test_segments_properties_random_streams():
+    """Size-independent properties on random token streams: every text token is kept exactly once and in order, times are
+    ordered, inside the window, and segments do not overlap."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    for case in range(200):
+        n = int(rng.integers(0, 60))
+        toks = []
+        for _ in range(n):
+            u = rng.random()
+            if u < 0.25:
+                toks.append(ts(float(rng.integers(0, 1500)) * 0.02))
+            elif u < 0.30:
+                toks.append(int(rng.integers(EOS, TSB)))            # special token
+            else:
+                toks.append(int(rng.integers(0, EOS)))
+        w0, wl = 30.0 * case, float(rng.integers(1, 31))
+        segs = segments_from_tokens(toks, TSB, EOS, w0, wl)
+        assert [t for s in segs for t in s[2]] == [t for t in toks if t < EOS]
+        for s0, s1, ids in segs:
+            assert ids and w0 <= s0 <= w0 + wl + 1e-9 and w0 <= s1 <= w0 + wl + 1e-9
