@@ -182,15 +182,12 @@ TW_API int tw_debug_self_attention_paged(tw_ctx* ctx, const void* q, int64_t q_s
 TW_API int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_col0, const void* kv, int64_t kv_ld, int k_col0,
                               int v_col0, void* out, int B, int Sq, int Sk, int H, int dtype, int impl, int causal, void* stream);
 
-/* Test / profiling switch (calling thread): the tw_debug_* attention entry points use the small-footprint kernel
- * variants of the split decode (3-stage K|V stream, 64-register self-attention). */
-TW_API void tw_debug_set_lite(int on);
 /* Test / profiling switch (calling thread): tw_debug_* launches carry the programmatic-dependent-launch attribute. */
 TW_API void tw_debug_set_pdl(int on);
 
 /* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
  * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,
- * 2: mma.sync skinny kernel for M <= 64, 3: tcgen05 skinny kernel for M <= 64 with K % 64 == 0, 4: its small-footprint variant for M <= 32 used by the split decode, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
+ * 3: tcgen05 skinny kernel for M <= 64 with K % 64 == 0, 0: CUDA-core kernel) or TW_F32 (CUDA-core check-mode kernel).  epi_mode: 0 store (dtype), 1 GELU
  * (dtype), 2 C(f32) += , 3 C(f32) = GELU(.) + pos[row % pos_period], 4 C(f32) = . */
 TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
                   int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);

@@ -181,8 +181,8 @@ template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_b
 // held in registers, online softmax, P.V accumulation, all in fp32.  At the end of a clip segment the
 // warps merge through shared memory (tree merge, 4-record buffer) and emit one partial record (m, l, o[64])
 // per head; a small second kernel merges the records of a clip.  Record index = cta + clip (unique, <= G + B - 2).
-// Variants measured on B200 and rejected (profiles/r01_split_decode.md): 8 warps with the refill issued by the last
-// warp to release a stage (shared-memory counter), and warp-private rings of single-row copies — both 10-15 % slower.
+// Variants measured on B200 and rejected (profiles/r01_split_decode.md): the refill issued by the last warp to release a
+// stage (shared-memory counter), and warp-private rings of single-row copies — both 10-15 % slower.
 constexpr int DA_WARPS = 8;        // consumer warps == rows per stage
 constexpr int DA_MAXSLOT = 5;      // ceil(H*8/32) with H <= 20
 constexpr int DA_PSTRIDE = HD + 2; // partial record: m, l, o[64]
@@ -254,7 +254,7 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
     p.G = g;
     p.R = ceil_div(total_rows, g);
     const size_t stage_bytes = (size_t)nw * 2 * H * HD * esz;
-    const size_t merge_bytes = (size_t)(nw == 8 ? 8 : 4) * H * DA_PSTRIDE * sizeof(float);
+    const size_t merge_bytes = (size_t)nw * H * DA_PSTRIDE * sizeof(float);
     int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
     if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
     if (st > max_stages) st = max_stages;
@@ -264,21 +264,19 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
     return p;
 }
 
-// NW = consumer warps = rows per stage.  8 (+ the producer warp = 9 warps) is the unsplit decode; 7 (+ producer = 8 warps:
-// exactly two warps per SM sub-partition) is the split decode, where the CTA must leave registers in every sub-partition
-// for the decode-step kernels of another sub-batch (profiles/r01_split_decode.md).
-template <typename T, int NW>
-// launch bound 384 for NW = 7 only caps the registers at 168 (65536 / 384), the count the 9-warp variant uses
-__global__ void __launch_bounds__(NW == 7 ? 384 : (NW + 1) * 32, 1)
+// NW = consumer warps = rows per stage (+ the producer warp = 9 warps)
+template <typename T>
+__global__ void __launch_bounds__((DA_WARPS + 1) * 32, 1)
 decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                         const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial) {
+    constexpr int NW = DA_WARPS;
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
     const int row_elems = 2 * d;
     const uint32_t stage_bytes = (uint32_t)NW * row_elems * sizeof(T);
     T* ring = reinterpret_cast<T*>(da_raw);
     float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)(NW == 8 ? 8 : 4) * H * DA_PSTRIDE * sizeof(float));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)NW * H * DA_PSTRIDE * sizeof(float));
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + DA_MAX_STAGES;
 
@@ -392,96 +390,40 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
             if (lane == 0) da_mbar_arrive(da_smem_u32(&empty_bar[stage]));
             if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (NW == 8) {
-            // unsplit decode: all 8 warps post their records, then 256 threads reduce them in parallel (shortest tail;
-            // the tree merge below costs ~2 us more per launch in situ)
-            // ---- merge the 8 warps of this clip segment -> one partial record per head
-    #pragma unroll
-            for (int s = 0; s < DA_MAXSLOT; ++s) {
-                const int slot = lane + 32 * s;
-                if (slot < nslots) {
-                    const int h = slot >> 3, e0 = (slot & 7) * 8;
-                    float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
-                    if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
-    #pragma unroll
-                    for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
-            for (int i = threadIdx.x; i < H * HD; i += NW * 32) {
-                const int h = i / HD, e = i % HD;
-                float m = -INFINITY;
-    #pragma unroll
-                for (int w = 0; w < NW; ++w) m = fmaxf(m, merge[((size_t)w * H + h) * DA_PSTRIDE]);
-                float l = 0.0f, o = 0.0f;
-    #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const float* rec = merge + ((size_t)w * H + h) * DA_PSTRIDE;
-                    const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
-                    l += rec[1] * sc;
-                    o += rec[2 + e] * sc;
-                }
-                float* prec = prec_base + (size_t)h * DA_PSTRIDE;
-                if (e == 0) { prec[0] = m; prec[1] = l; }
-                prec[2 + e] = o;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-        } else {
-            // ---- merge the 8 warps of this clip segment -> one partial record per head.  Tree merge through a
-            // 4-record buffer (warps 4-7 -> 0-3, 2-3 -> 0-1, 1 -> 0): half the shared memory of an 8-record buffer,
-            // which is what lets a decode-step GEMM CTA of the other sub-batch share the SM (model.cu, split decode).
-    #pragma unroll
-            for (int half = 4; half >= 1; half >>= 1) {
-                if (warp >= half && warp < 2 * half && warp < NW) {
-    #pragma unroll
-                    for (int s = 0; s < DA_MAXSLOT; ++s) {
-                        const int slot = lane + 32 * s;
-                        if (slot < nslots) {
-                            const int h = slot >> 3, e0 = (slot & 7) * 8;
-                            float* rec = merge + ((size_t)(warp - half) * H + h) * DA_PSTRIDE;
-                            if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
-    #pragma unroll
-                            for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-                if (warp < half && warp + half < NW) {
-    #pragma unroll
-                    for (int s = 0; s < DA_MAXSLOT; ++s) {
-                        const int slot = lane + 32 * s;
-                        if (slot < nslots) {
-                            const int h = slot >> 3, e0 = (slot & 7) * 8;
-                            const float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
-                            const float m2 = rec[0], l2 = rec[1];
-                            const float m_new = fmaxf(mrun[s], m2);
-                            const float sc1 = (mrun[s] == -INFINITY) ? 0.0f : __expf(mrun[s] - m_new);
-                            const float sc2 = (m2 == -INFINITY) ? 0.0f : __expf(m2 - m_new);
-                            lrun[s] = lrun[s] * sc1 + l2 * sc2;
-                            mrun[s] = m_new;
-    #pragma unroll
-                            for (int e = 0; e < 8; ++e) of[s][e] = of[s][e] * sc1 + rec[2 + e0 + e] * sc2;
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
-            }
-            if (warp == 0) {
-                float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
-    #pragma unroll
-                for (int s = 0; s < DA_MAXSLOT; ++s) {
-                    const int slot = lane + 32 * s;
-                    if (slot < nslots) {
-                        const int h = slot >> 3, e0 = (slot & 7) * 8;
-                        float* prec = prec_base + (size_t)h * DA_PSTRIDE;
-                        if ((slot & 7) == 0) { prec[0] = mrun[s]; prec[1] = lrun[s]; }
-    #pragma unroll
-                        for (int e = 0; e < 8; e += 2) *reinterpret_cast<float2*>(prec + 2 + e0 + e) = make_float2(of[s][e], of[s][e + 1]);
-                    }
-                }
+        // unsplit decode: all 8 warps post their records, then 256 threads reduce them in parallel (shortest tail;
+        // the tree merge below costs ~2 us more per launch in situ)
+        // ---- merge the 8 warps of this clip segment -> one partial record per head
+#pragma unroll
+        for (int s = 0; s < DA_MAXSLOT; ++s) {
+            const int slot = lane + 32 * s;
+            if (slot < nslots) {
+                const int h = slot >> 3, e0 = (slot & 7) * 8;
+                float* rec = merge + ((size_t)warp * H + h) * DA_PSTRIDE;
+                if ((slot & 7) == 0) { rec[0] = mrun[s]; rec[1] = lrun[s]; }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rec[2 + e0 + e] = of[s][e];
             }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+        float* prec_base = partial + ((size_t)blockIdx.x + b) * H * DA_PSTRIDE;
+        for (int i = threadIdx.x; i < H * HD; i += NW * 32) {
+            const int h = i / HD, e = i % HD;
+            float m = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) m = fmaxf(m, merge[((size_t)w * H + h) * DA_PSTRIDE]);
+            float l = 0.0f, o = 0.0f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float* rec = merge + ((size_t)w * H + h) * DA_PSTRIDE;
+                const float sc = (rec[0] == -INFINITY) ? 0.0f : __expf(rec[0] - m);
+                l += rec[1] * sc;
+                o += rec[2 + e] * sc;
+            }
+            float* prec = prec_base + (size_t)h * DA_PSTRIDE;
+            if (e == 0) { prec[0] = m; prec[1] = l; }
+            prec[2 + e] = o;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
         r = seg_end;
     }
 }
@@ -539,10 +481,9 @@ template <> struct Ld8<__nv_bfloat16> {
     }
 };
 
-// SA_UNR = rows in flight per warp.  The <T, 2> variant is capped at 64 registers so that a CTA fits next to a resident
-// cross-attention streaming CTA of the other sub-batch (split decode, model.cu).
+// SA_UNR = rows in flight per warp
 template <typename T, int SA_UNR>
-__global__ void __launch_bounds__(SA_WARPS * 32, SA_UNR == 2 ? 4 : (sizeof(T) == 2 ? 3 : 1))   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
+__global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 3 : 1)   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out, const int32_t* __restrict__ page_table,
                              int pt_stride) {
@@ -643,11 +584,7 @@ template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                            T* out, cudaStream_t st, const int32_t* page_table, int pt_stride) {
     dim3 grid(ceil_div(H, SA_HG), B);
-    if (g_decode_lite && sizeof(T) == 2)
-        launch_k(self_attention_decode_kernel<T, 2>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
-                 page_table, pt_stride);
-    else
-        launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
+    launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
                  page_table, pt_stride);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
@@ -668,49 +605,28 @@ size_t decode_attention_partial_floats(int B, int H) {
 
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, bool stream_pdl) {
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
     (void)decode_attention_partial_floats(B, H);
-    // split decode ("lite"): 7 consumer warps and 3 stages (129 KB with the merge buffer, two warps per SM sub-partition) leave
-    // room for a decode-step GEMM CTA of another sub-batch on the same SM
-    const bool lite = g_decode_lite;
     static const int env_stages = getenv("TWB200_DA_STAGES") ? atoi(getenv("TWB200_DA_STAGES")) : 0;      // tuning knob
-    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, lite ? 3 : (env_stages >= 2 ? env_stages : DA_MAX_STAGES), lite ? 7 : 8);
+    DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, env_stages >= 2 ? env_stages : DA_MAX_STAGES, DA_WARPS);
     if (d_tk) p.G = g_da_sm_count;               // row count only known on the device: launch every CTA
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
-        cudaFuncSetAttribute(decode_attention_stream<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(decode_attention_stream<T, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        // keep the SM's shared-memory carveout at its maximum so that CTAs of other decode-step kernels fit next to this one
-        if (!(getenv("TWB200_CARVEOUT") && atoi(getenv("TWB200_CARVEOUT")) == 0))
-            cudaFuncSetAttribute(decode_attention_stream<T, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(decode_attention_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         attr_set[which] = true;
     }
     if (ev0) cudaEventRecord(ev0, st);
     const int kv_static = d_tk ? 0 : 1;
-    // stream_pdl = false (split decode): as a programmatic dependent the CTAs would become resident — 129 KB of shared
-    // memory each — while their predecessor still runs, and keep the other sub-batch's streaming CTAs off the SMs
-    const bool pdl_saved = g_pdl;
-    if (!stream_pdl) g_pdl = false;
-    if (lite)
-        launch_k(decode_attention_stream<T, 7>, dim3(p.G), dim3(8 * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
-                 p.stages, kv_static, partial);
-    else
-        launch_k(decode_attention_stream<T, 8>, dim3(p.G), dim3(9 * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
-                 p.stages, kv_static, partial);
-    g_pdl = pdl_saved;
+    launch_k(decode_attention_stream<T>, dim3(p.G), dim3((DA_WARPS + 1) * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
+             p.stages, kv_static, partial);
     if (ev1) cudaEventRecord(ev1, st);
-    // measured (A/B, large-v3, 64 clips): 256-thread CTAs (4 heads) 1222.7 ms per decode vs 1229.8 ms with 64-thread CTAs;
-    // 640-thread CTAs: no further gain
-    static const int combine_hpc = getenv("TWB200_COMBINE_HPC") ? atoi(getenv("TWB200_COMBINE_HPC")) : 4;      // tuning knob
-    if (combine_hpc == 4)
-        launch_k(decode_attention_combine<T, 4>, dim3(ceil_div(H, 4), B), dim3(HD * 4), 0, st, partial, Tk, d_tk, B, p.G, H, out);
-    else
-        launch_k(decode_attention_combine<T, 1>, dim3(H, B), dim3(HD), 0, st, partial, Tk, d_tk, B, p.G, H, out);
+    // measured (A/B, large-v3, 64 clips): 256-thread CTAs (4 heads) 1222.7 ms per decode vs 1229.8 ms with 64-thread CTAs
+    launch_k(decode_attention_combine<T, 4>, dim3(ceil_div(H, 4), B), dim3(HD * 4), 0, st, partial, Tk, d_tk, B, p.G, H, out);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
-                                      cudaStream_t, cudaEvent_t, cudaEvent_t, bool);
+                                      cudaStream_t, cudaEvent_t, cudaEvent_t);
 template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*, int, int,
-                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t, bool);
+                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
 
 }  // namespace tw

@@ -82,9 +82,6 @@ __device__ __forceinline__ float warp_max(float v) {
 // barrier/TMEM setup and weight prefetch overlap the predecessor's tail.  Without the launch attribute both
 // instructions are no-ops.
 extern thread_local bool g_pdl;
-// set by the split decode (model.cu): decode-step kernels use their small-footprint variants (<= 64 KB shared memory,
-// <= 80 registers) so that they share an SM with a resident cross-attention streaming CTA of the other sub-batch
-extern thread_local bool g_decode_lite;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

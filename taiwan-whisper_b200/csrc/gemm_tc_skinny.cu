@@ -23,16 +23,14 @@ namespace tw {
 constexpr int SK2_THREADS = 192;
 constexpr int SK2_KSUB = 4;                   // K blocks (of 64) per TMA box / pipeline stage
 
-// AROWS = rows of the A box (64, or 32 for the "lite" variant used by the split decode: 2 stages x 32 KB and <= 80
-// registers per thread, so that one CTA fits next to a resident cross-attention streaming CTA of the other sub-batch).
+// AROWS = rows of the A box
 template <int BN, int AROWS> struct Sk2Cfg {
-    static constexpr bool LITE = (AROWS == 32);
     static constexpr int A_SUB = AROWS * 64 * 2;                           // A tile of one K block
     static constexpr int W_SUB = BN * 64 * 2;
     static constexpr int A_REGION = SK2_KSUB * A_SUB;
-    static constexpr int STAGE_BYTES = SK2_KSUB * (A_SUB + W_SUB);         // 48 KB (BN 32) / 64 KB (BN 64) / 32 KB (lite)
-    static constexpr int STAGES = LITE ? 2 : ((BN == 32) ? 4 : 3);
-    static constexpr int MIN_CTAS = LITE ? 4 : 1;                          // register cap: 65536 / (192 * 4) -> 80
+    static constexpr int STAGE_BYTES = SK2_KSUB * (A_SUB + W_SUB);         // 48 KB (BN 32) / 64 KB (BN 64)
+    static constexpr int STAGES = (BN == 32) ? 4 : 3;
+    static constexpr int MIN_CTAS = 1;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
     // the MMA runs as M = 128 and reads 128 x 128 B from the start of every A tile: the read of the last tile must stay
@@ -320,9 +318,6 @@ int gemm_tc_skinny_init(tw_ctx* ctx) {
     }
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32, 64>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<64, 64>::SMEM_BYTES));
-    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32, 32>::SMEM_BYTES));
-    if (!(getenv("TWB200_CARVEOUT") && atoi(getenv("TWB200_CARVEOUT")) == 0))
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // probe once whether the driver accepts the 3-D view (K-block stride 128 B < row stride)
     static __nv_bfloat16* probe = nullptr;
     if (!probe) {
@@ -344,14 +339,12 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
         ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc_skinny: unsupported shape / alignment");
         return TW_E_UNSUPPORTED;
     }
-    // lite: set by the split decode (model.cu) — small enough to share an SM with a streaming cross-attention CTA
-    const bool lite = g_decode_lite && M <= 32;
     // 64-wide tiles once 32-wide ones would need more than `waves` passes over the SMs (tuning knob TWB200_SK_WAVES; 1 = measured default: 2, i.e. fc1 as 160 32-wide
     // tiles on 148 CTAs instead of 80 64-wide ones, is 12 ms per decode slower)
     static const int waves = getenv("TWB200_SK_WAVES") ? atoi(getenv("TWB200_SK_WAVES")) : 1;
-    const int BN = (!lite && ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
+    const int BN = (ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
     CUtensorMap ma, mw;
-    TW_CHECK(sk2_map(ctx, A, M, K, lda, lite ? 32 : 64, &ma));
+    TW_CHECK(sk2_map(ctx, A, M, K, lda, 64, &ma));
     TW_CHECK(sk2_map(ctx, W, N, K, ldw, BN, &mw));
     int tiles = ceil_div(N, BN);
     int ksplit = 1;
@@ -367,9 +360,7 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     // the kernel splits K in units of K blocks: make kb_per_split a multiple of KSUB by construction
     // (k_blocks_total / ksplit rounded up to whole stages)
-    if (lite)
-        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32, 32>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32, 32>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
-    else if (BN == 32)
+    if (BN == 32)
         TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     else
         TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<64, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<64, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));

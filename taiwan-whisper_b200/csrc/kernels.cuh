@@ -56,11 +56,6 @@ bool gemm_tc_skinny_supported(int M, int N, int K, const GemmEpi& epi);
 int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
                    const GemmEpi& epi, cudaStream_t st);
 
-// mma.sync weight-streaming GEMM for M <= 64 (gemm_skinny.cu), bf16; opt-in
-bool gemm_skinny_supported(int M, int N, int K, const GemmEpi& epi);
-int gemm_skinny(tw_ctx* ctx, const __nv_bfloat16* X, int64_t ldx, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
-                const GemmEpi& epi, cudaStream_t st);
-
 // ---- paged self-attention K|V cache: TW_KV_PAGE positions per page; page_table[clip * pt_stride + pos / TW_KV_PAGE] is the
 // physical page of a clip's logical page inside the layer's pool [n_pages][TW_KV_PAGE][2d]
 constexpr int TW_KV_PAGE = 16;
@@ -114,8 +109,7 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
 template <typename T>
 // d_tk (nullable): device int, the number of rows is *d_tk + 1 (self-attention cache at position pos) instead of Tk
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
-                      bool stream_pdl = true);
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 size_t decode_attention_partial_floats(int B, int H);
 // single-launch self-attention over the short decoder cache (Tk = *d_tk + 1 when d_tk is given)
 template <typename T>
@@ -139,7 +133,7 @@ struct DecodeState {
 };
 // one CTA per row: rules -> argmax -> finished/pad bookkeeping -> next input token
 // (inside the forced prompt it only feeds the next prompt token)
-void select_tokens(const float* logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
+void select_tokens(const float* logits, int64_t ld_logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
                    int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream);
 void decode_state_init(const DecodeState& st, int B, int first_tok, cudaStream_t stream);
 void set_cur_tok(const DecodeState& st, int B, int tok, cudaStream_t stream);

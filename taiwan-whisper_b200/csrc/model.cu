@@ -21,7 +21,6 @@ using namespace tw;
 
 namespace tw {
 thread_local bool g_pdl = false;
-thread_local bool g_decode_lite = false;
 }
 
 namespace {
@@ -83,13 +82,12 @@ struct LayerW {
 }  // namespace
 
 struct GraphKey {
-    int B, eos, pad, ts_begin, no_ts, max_init, nsplit;
+    int B, eos, pad, ts_begin, no_ts, max_init;
     bool operator<(const GraphKey& o) const {
-        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, nsplit) <
-               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.nsplit);
+        return std::tie(B, eos, pad, ts_begin, no_ts, max_init) <
+               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init);
     }
 };
-constexpr int TW_MAX_SPLIT = 4;
 struct GraphEntry {
     cudaGraphExec_t exec;
     uint64_t kernels;
@@ -101,7 +99,6 @@ struct tw_model {
     int esz = 2;                 // bytes per element of the model dtype
     bool use_tc = false;         // tcgen05 GEMMs (bf16 only)
     bool use_tc_attn = false;    // tcgen05 encoder attention (bf16 only)
-    bool use_skinny = false;     // mma.sync skinny GEMM for decode steps (bf16 only, opt-in)
     bool use_tc_skinny = true;   // tcgen05 skinny GEMM with multi-K-block TMA boxes for M <= 64
     std::vector<void*> allocs;
     size_t bytes = 0;
@@ -126,6 +123,7 @@ struct tw_model {
     int32_t* d_page_table = nullptr;
     int32_t* h_page_table = nullptr;   // pinned staging
     float *dx = nullptr, *dlogits = nullptr, *dpartial = nullptr;
+    int64_t ld_logits = 0;     // row pitch of dlogits: vocab rounded up to 4 floats (16-byte rows for the TMA-store epilogue)
     void *dxn = nullptr, *dqkv = nullptr, *datt = nullptr, *dq = nullptr, *dhmid = nullptr;
     int32_t* dstate = nullptr;  // 6*maxB + 1 ints
     uint8_t *d_suppress = nullptr, *d_begin_suppress = nullptr;
@@ -138,19 +136,10 @@ struct tw_model {
     bool use_pdl = true;         // programmatic dependent launch inside the decode step
     cudaStream_t cap_stream = nullptr;
     std::map<GraphKey, GraphEntry> graphs;
-    // split decode: the decoder layers of one step run as `nsplit` independent sub-batches on their own streams (forked
-    // from / joined into the step's stream, also inside the captured graph), so that the latency-bound kernel chain of
-    // one sub-batch can overlap the HBM-bound cross-attention K/V stream of another.  Opt-in: TWB200_SPLIT = 2..4.
-    int split = 0;
-    cudaStream_t sub_stream[TW_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[TW_MAX_SPLIT] = {nullptr, nullptr, nullptr, nullptr};
-    size_t partial_stride = 0;   // floats per sub-batch region of dpartial
     double prof_bytes = 0.0;     // K|V bytes of one profiled cross-attention launch
     // debug timeline (TWB200_TRACE=<position>): CUDA events after every kernel of two middle decoder layers at that
     // position (non-graph path only), printed to stderr at the end of the decode call
     int trace_pos = -1;
-    int split_pdl = 0;           // PDL inside the split layers: 0 none (measured best), 1 all but the K|V stream kernel, 2 all (TWB200_SPLIT_PDL)
-    bool lite = true;            // small-footprint kernel variants in the split decode (TWB200_LITE=0 disables)
     std::vector<std::pair<cudaEvent_t, std::string>> trace;
     // in-situ timing of the dominant kernel (cross-attention K/V streaming) for bench.py's roofline
     bool prof_on = false;
@@ -339,10 +328,11 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, &m->datt, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dq, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dhmid, B * D.ffn * e));
-    TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * D.vocab * sizeof(float)));
-    m->partial_stride = decode_attention_partial_floats((int)B, D.heads);
-    TW_CHECK(dev_alloc(m, (void**)&m->dpartial, TW_MAX_SPLIT * m->partial_stride * sizeof(float)));
-    TW_CUDA_OK(m->ctx, cudaMemset(m->dpartial, 0, TW_MAX_SPLIT * m->partial_stride * sizeof(float)));
+    m->ld_logits = ((int64_t)D.vocab + 3) / 4 * 4;
+    TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * (size_t)m->ld_logits * sizeof(float)));
+    const size_t partial_floats = decode_attention_partial_floats((int)B, D.heads);
+    TW_CHECK(dev_alloc(m, (void**)&m->dpartial, partial_floats * sizeof(float)));
+    TW_CUDA_OK(m->ctx, cudaMemset(m->dpartial, 0, partial_floats * sizeof(float)));
     TW_CHECK(dev_alloc(m, (void**)&m->dstate, (6 * B + 4) * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
     TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
@@ -354,11 +344,6 @@ int alloc_workspace(tw_model* m) {
     TW_CUDA_OK(m->ctx, cudaMallocHost(&m->h_step, STEP_INTS * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_step, STEP_INTS * sizeof(int32_t)));
     TW_CUDA_OK(m->ctx, cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
-    for (int h = 0; h < TW_MAX_SPLIT; ++h) {
-        TW_CUDA_OK(m->ctx, cudaStreamCreateWithFlags(&m->sub_stream[h], cudaStreamNonBlocking));
-        TW_CUDA_OK(m->ctx, cudaEventCreateWithFlags(&m->ev_join[h], cudaEventDisableTiming));
-    }
-    TW_CUDA_OK(m->ctx, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
     return TW_OK;
 }
 
@@ -377,7 +362,6 @@ template <>
 int gemm<__nv_bfloat16>(tw_model* m, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, int64_t ldw, int M, int N, int K,
                         const GemmEpi& epi, cudaStream_t st) {
     m->ctx->launches += 1;
-    if (m->use_tc && m->use_skinny && gemm_skinny_supported(M, N, K, epi)) return gemm_skinny(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     if (m->use_tc && m->use_tc_skinny && gemm_tc_skinny_supported(M, N, K, epi)) return gemm_tc_skinny(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     if (m->use_tc) return gemm_tc(m->ctx, A, lda, W, ldw, M, N, K, epi, st);
     gemm_simt<__nv_bfloat16>(A, lda, W, ldw, M, N, K, epi, st);
@@ -553,11 +537,8 @@ struct StepIo {
 
 // One decode step (all kernels of one token position).  Position, prompt and output stride are read from
 // m->d_step on the device, so the same launch sequence — or one captured CUDA graph — serves every position.
-// nsplit > 1: the decoder layers run as nsplit sub-batches of rows, each on its own stream (fork after the embedding,
-// join before the final LayerNorm); the sub-batches touch disjoint rows of every buffer and share only the weights.
 template <typename T>
-int launch_step(tw_model* m, int B, int nsplit, const RulesDev& R, const DecodeState& S, const StepIo& io, cudaStream_t st,
-                bool trace = false) {
+int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, const StepIo& io, cudaStream_t st, bool trace = false) {
     const tw_model_desc& D = m->desc;
     tw_ctx* ctx = m->ctx;
     const int d = D.d_model, V = D.vocab, H = D.heads;
@@ -567,117 +548,76 @@ int launch_step(tw_model* m, int B, int nsplit, const RulesDev& R, const DecodeS
     const size_t cross_layer = (size_t)D.max_batch * TW_N_CTX * 2 * d;
     const int32_t* d_pos = m->d_step + STEP_POS;
     // PDL only on the bf16 product path: every kernel launched below goes through launch_k and executes pdl_wait()
-    const bool pdl_base = m->use_pdl && sizeof(T) == 2 && m->use_tc && !m->use_skinny;
-    const bool pdl_on = pdl_base && (nsplit == 1 || m->split_pdl >= 1);       // inside the (split) layers
+    const bool pdl_on = m->use_pdl && sizeof(T) == 2 && m->use_tc;
     struct FlagScope {
-        FlagScope(bool pdl, bool lite) { g_pdl = pdl; g_decode_lite = lite; }
-        ~FlagScope() { g_pdl = false; g_decode_lite = false; }
-    } flag_scope(pdl_base, nsplit > 1 && sizeof(T) == 2 && m->lite);
-    auto mark = [&](int l, int h, const char* name, cudaStream_t ss) {
+        explicit FlagScope(bool pdl) { g_pdl = pdl; }
+        ~FlagScope() { g_pdl = false; }
+    } flag_scope(pdl_on);
+    auto mark = [&](int l, const char* name) {
         if (!trace || (l >= 0 && l != D.dec_layers / 2 && l != D.dec_layers / 2 + 1)) return;
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
-        cudaEventRecord(e, ss);
-        m->trace.emplace_back(e, "L" + std::to_string(l) + " h" + std::to_string(h) + " " + name);
+        cudaEventRecord(e, st);
+        m->trace.emplace_back(e, "L" + std::to_string(l) + " " + name);
     };
     embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, m->d_step, x, B, d, st);
-    mark(-1, 0, "embed", st);
-    g_pdl = pdl_on;
-    cudaStream_t sub[TW_MAX_SPLIT] = {st, st, st, st};
-    int r0[TW_MAX_SPLIT + 1] = {0, B, B, B, B};
-    if (nsplit > 1) {
-        TW_CUDA_OK(ctx, cudaEventRecord(m->ev_fork, st));
-        for (int h = 0; h < nsplit; ++h) {
-            sub[h] = m->sub_stream[h];
-            TW_CUDA_OK(ctx, cudaStreamWaitEvent(sub[h], m->ev_fork, 0));
-            r0[h] = (int)((int64_t)B * h / nsplit);
-        }
-        r0[nsplit] = B;
-    }
+    mark(-1, "embed");
+    const int32_t* pt = m->d_page_table;
     for (int l = 0; l < D.dec_layers; ++l) {
         const LayerW& L = m->dec[l];
-        for (int h = 0; h < nsplit; ++h) {
-            const int b0 = r0[h], Bh = r0[h + 1] - r0[h];
-            cudaStream_t ss = sub[h];
-            float* xh = x + (size_t)b0 * d;
-            T* xnh = xn + (size_t)b0 * d; T* qkvh = qkv + (size_t)b0 * 3 * d; T* atth = att + (size_t)b0 * d;
-            T* qh = q + (size_t)b0 * d; T* hmidh = hmid + (size_t)b0 * D.ffn;
-            T* cache = (T*)m->self_kv + l * self_layer;                       // the layer's page pool
-            const int32_t* pt = m->d_page_table + (size_t)b0 * m->kv_pages;   // page table rows of this sub-batch
-            // the first kernel after the fork depends on another stream's work: a full (not programmatic) dependency
-            if (nsplit > 1 && l == 0) g_pdl = false;
-            layernorm<T>(xh, L.ln1_g, L.ln1_b, xnh, Bh, d, ss);
-            mark(l, h, "ln1", ss);
-            g_pdl = pdl_on;
-            GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkvh, 3 * d);
-            const bool fused_append = (sizeof(T) == 2) && m->use_tc && (d % 32 == 0);
-            if (fused_append) {      // the K|V columns of the fused QKV projection land in the cache row of this position
-                qe.n_split = d;
-                qe.C2 = cache;
-                qe.ldc2 = 0;
-                qe.d_row2 = d_pos;
-                qe.row2_stride = 2 * d;
-                qe.page_table = pt;
-                qe.pt_stride = m->kv_pages;
-            }
-            TW_CHECK(gemm<T>(m, xnh, d, (const T*)L.self.qkv_w, d, Bh, 3 * d, d, qe, ss));
-            mark(l, h, "qkv", ss);
-            if (!fused_append) { kv_append<T>(qkvh, cache, m->d_step, Bh, d, D.max_target, ss, pt, m->kv_pages); ctx->launches += 1; }
-            self_attention_decode<T>(qkvh, 3 * d, cache, 0, 0, d_pos, Bh, H, atth, ss, pt, m->kv_pages);
-            mark(l, h, "self_attn", ss);
-            TW_CHECK(gemm<T>(m, atth, d, (const T*)L.self.o_w, d, Bh, d, d, mk_epi(EPI_RESID, L.self.o_b, xh, d), ss));
-            mark(l, h, "self_o", ss);
-            layernorm<T>(xh, L.ln2_g, L.ln2_b, xnh, Bh, d, ss);
-            mark(l, h, "ln2", ss);
-            TW_CHECK(gemm<T>(m, xnh, d, (const T*)L.cross.q_w, d, Bh, d, d, mk_epi(EPI_STORE, L.cross.q_b, qh, d), ss));
-            mark(l, h, "cross_q", ss);
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (m->prof_on && h == 0 && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
-                e0 = m->prof_ev[m->prof_used];
-                e1 = m->prof_ev[m->prof_used + 1];
-                m->prof_used += 2;
-                m->prof_bytes = (double)Bh * TW_N_CTX * 2 * d * sizeof(T);
-            }
-            decode_attention<T>(qh, d, (const T*)m->xkv + l * cross_layer + (size_t)b0 * TW_N_CTX * 2 * d, (int64_t)TW_N_CTX * 2 * d,
-                                TW_N_CTX, nullptr, Bh, H, m->dpartial + (size_t)h * m->partial_stride, atth, ss, e0, e1,
-                                nsplit == 1 || m->split_pdl >= 2);
-            mark(l, h, "cross_attn+combine", ss);
-            TW_CHECK(gemm<T>(m, atth, d, (const T*)L.cross.o_w, d, Bh, d, d, mk_epi(EPI_RESID, L.cross.o_b, xh, d), ss));
-            mark(l, h, "cross_o", ss);
-            layernorm<T>(xh, L.ln3_g, L.ln3_b, xnh, Bh, d, ss);
-            mark(l, h, "ln3", ss);
-            TW_CHECK(gemm<T>(m, xnh, d, (const T*)L.fc1_w, d, Bh, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmidh, D.ffn), ss));
-            mark(l, h, "fc1", ss);
-            TW_CHECK(gemm<T>(m, hmidh, D.ffn, (const T*)L.fc2_w, D.ffn, Bh, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, xh, d), ss));
-            mark(l, h, "fc2", ss);
-            ctx->launches += 6;       // 3 LN, self-attention, cross-attention stream + combine; the GEMMs count themselves
+        T* cache = (T*)m->self_kv + l * self_layer;                       // the layer's page pool
+        layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
+        mark(l, "ln1");
+        GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d);
+        // the K|V columns of the fused QKV projection land in the cache row of this position — only the skinny tcgen05
+        // kernel (M <= 64) implements the column split; larger batches append with a separate kernel
+        const bool fused_append = (sizeof(T) == 2) && m->use_tc && m->use_tc_skinny && gemm_tc_skinny_supported(B, 3 * d, d, qe);
+        if (fused_append) {
+            qe.n_split = d;
+            qe.C2 = cache;
+            qe.ldc2 = 0;
+            qe.d_row2 = d_pos;
+            qe.row2_stride = 2 * d;
+            qe.page_table = pt;
+            qe.pt_stride = m->kv_pages;
         }
-    }
-    if (nsplit > 1) {
-        for (int h = 0; h < nsplit; ++h) {
-            TW_CUDA_OK(ctx, cudaEventRecord(m->ev_join[h], sub[h]));
-            TW_CUDA_OK(ctx, cudaStreamWaitEvent(st, m->ev_join[h], 0));
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
+        mark(l, "qkv");
+        if (!fused_append) { kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st, pt, m->kv_pages); ctx->launches += 1; }
+        self_attention_decode<T>(qkv, 3 * d, cache, 0, 0, d_pos, B, H, att, st, pt, m->kv_pages);
+        mark(l, "self_attn");
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+        mark(l, "self_o");
+        layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
+        mark(l, "ln2");
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+        mark(l, "cross_q");
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (m->prof_on && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
+            e0 = m->prof_ev[m->prof_used];
+            e1 = m->prof_ev[m->prof_used + 1];
+            m->prof_used += 2;
+            m->prof_bytes = (double)B * TW_N_CTX * 2 * d * sizeof(T);
         }
-        g_pdl = false;                // the first kernel after the join: full dependency on every sub-batch
-        g_decode_lite = false;
+        decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial, att,
+                            st, e0, e1);
+        mark(l, "cross_attn+combine");
+        TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
+        mark(l, "cross_o");
+        layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
+        mark(l, "ln3");
+        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+        mark(l, "fc1");
+        TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+        mark(l, "fc2");
+        ctx->launches += 6;       // 3 LN, self-attention, cross-attention stream + combine; the GEMMs count themselves
     }
     layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
-    g_pdl = pdl_base;
-    TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, V), st));
-    select_tokens(m->dlogits, V, B, m->d_step, R, S, io.out_tokens, io.out_lengths, io.forced, io.logits_tap, st);
+    TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, m->ld_logits), st));
+    select_tokens(m->dlogits, m->ld_logits, V, B, m->d_step, R, S, io.out_tokens, io.out_lengths, io.forced, io.logits_tap, st);
     advance_step(m->d_step, st);
     ctx->launches += 4;           // embed, LN, select, advance
     return TW_OK;
-}
-
-// number of sub-batches the decoder layers of a step are split into (see tw_model::split).  Off unless TWB200_SPLIT >= 2:
-// measured on B200 (profiles/r01_split_decode.md) the split only pays when the streaming CTA leaves register room in
-// every SM sub-partition, which costs the K|V stream kernel more (10-15 %) than the overlap returns.
-int pick_nsplit(const tw_model* m, int B) {
-    int n = m->split <= 1 ? 1 : m->split;
-    if (n > TW_MAX_SPLIT) n = TW_MAX_SPLIT;
-    if (n > B) n = B;
-    return n < 1 ? 1 : n;
 }
 
 template <typename T>
@@ -725,8 +665,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     StepIo io{out_tokens, out_lengths, forced, logits_tap};
     if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
     if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
-    const int nsplit = pick_nsplit(m, B);
-    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, nsplit};
+    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts};
     cudaGraphExec_t exec = nullptr;
     uint64_t exec_kernels = 0;
 
@@ -745,7 +684,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
                 cudaGraph_t graph = nullptr;
                 const uint64_t l0 = ctx->launches;
                 TW_CUDA_OK(ctx, cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-                int rc = launch_step<T>(m, B, nsplit, R, S, io, m->cap_stream);
+                int rc = launch_step<T>(m, B, R, S, io, m->cap_stream);
                 cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
                 if (rc != TW_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess || !graph) {
@@ -767,7 +706,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
             TW_CUDA_OK(ctx, cudaGraphLaunch(exec, st));
             ctx->launches += exec_kernels;
         } else {
-            TW_CHECK(launch_step<T>(m, B, nsplit, R, S, io, st, pos == m->trace_pos));
+            TW_CHECK(launch_step<T>(m, B, R, S, io, st, pos == m->trace_pos));
         }
         ++steps_done;
         const int g = pos - (P - 1);
@@ -799,7 +738,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     }
     if (!m->trace.empty()) {
         cudaStreamSynchronize(st);
-        fprintf(stderr, "[twb200 trace] position %d, B=%d, nsplit=%d (ms since the embed kernel finished)\n", m->trace_pos, B, nsplit);
+        fprintf(stderr, "[twb200 trace] position %d, B=%d (us since the embed kernel finished)\n", m->trace_pos, B);
         for (size_t i = 1; i < m->trace.size(); ++i) {
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, m->trace[0].first, m->trace[i].first);
@@ -897,19 +836,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_tc_skinny = !(g3 && strcmp(g3, "0") == 0);
     const char* gp = getenv("TWB200_PDL");
     m->use_pdl = !(gp && strcmp(gp, "0") == 0);
-    const char* gsp = getenv("TWB200_SPLIT");
-    m->split = gsp ? atoi(gsp) : 0;
-    if (m->split < 0 || m->split > TW_MAX_SPLIT) m->split = 0;
     const char* gtr = getenv("TWB200_TRACE");
     m->trace_pos = gtr ? atoi(gtr) : -1;
-    const char* gsq = getenv("TWB200_SPLIT_PDL");
-    if (gsq) m->split_pdl = atoi(gsq);
-    const char* gl = getenv("TWB200_LITE");
-    m->lite = !(gl && strcmp(gl, "0") == 0);
-    const char* gs = getenv("TWB200_SKINNY");
-    // measured on B200 (profiles/r01_decode_kernels_ncu.md): the tcgen05 N=32-tile kernel beats the mma.sync skinny
-    // kernel at every decode shape, so the skinny kernel is opt-in (TWB200_SKINNY=1) until it is reworked
-    m->use_skinny = m->use_tc && (gs && strcmp(gs, "1") == 0);
     WeightTable wt;
     for (size_t i = 0; i < n; ++i)
         if (table[i].name) wt.by_name[table[i].name] = &table[i];
@@ -931,11 +859,6 @@ void tw_model_free(tw_model* m) {
     if (m->h_page_table) cudaFreeHost(m->h_page_table);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
-    for (int h = 0; h < TW_MAX_SPLIT; ++h) {
-        if (m->sub_stream[h]) cudaStreamDestroy(m->sub_stream[h]);
-        if (m->ev_join[h]) cudaEventDestroy(m->ev_join[h]);
-    }
-    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     for (auto& ev : m->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : m->prof_ev) cudaEventDestroy(ev);
@@ -968,8 +891,8 @@ size_t tw_workspace_bytes(const tw_model_desc* desc) {
                 al(B * TW_N_FRAMES * 3 * D.n_mel * e) + al(B * TW_N_FRAMES * d * e) + al(M * 3 * d * e) + al(M * d * f4) +
                 al(M * d * e) + al(M * d * e) + al(M * ffn * e) + al(M * d * e) + al((size_t)D.dec_layers * M * 2 * d * e) +
                 al((size_t)D.dec_layers * B * kv_pages * TW_KV_PAGE * 2 * d * e) + al(B * kv_pages * sizeof(int32_t)) +
-                al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * V * f4) +
-                al(TW_MAX_SPLIT * decode_attention_partial_floats((int)B, D.heads) * f4) + al((6 * B + 4) * sizeof(int32_t)) + al(V) + al(V) +
+                al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * ((V + 3) / 4 * 4) * f4) +
+                al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((6 * B + 4) * sizeof(int32_t)) + al(V) + al(V) +
                 al(4096 * sizeof(int32_t)) + al(B * D.max_target * sizeof(int32_t)) + al(B * sizeof(int32_t)) + al(STEP_INTS * sizeof(int32_t));
     return w + ws;
 }
@@ -1108,13 +1031,6 @@ int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, 
         gemm_simt<float>((const float*)A, K, (const float*)W, K, M, N, K, e, st);
     } else if (dtype == TW_BF16) {
         if (use_tc == 3) return gemm_tc_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
-        if (use_tc == 4) {       // small-footprint variant of the split decode (M <= 32)
-            g_decode_lite = true;
-            const int r = gemm_tc_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
-            g_decode_lite = false;
-            return r;
-        }
-        if (use_tc == 2) return gemm_skinny(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         if (use_tc) return gemm_tc(ctx, (const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
         gemm_simt<__nv_bfloat16>((const __nv_bfloat16*)A, K, (const __nv_bfloat16*)W, K, M, N, K, e, st);
     } else {
@@ -1217,7 +1133,6 @@ int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_col0, con
     return TW_OK;
 }
 
-void tw_debug_set_lite(int on) { g_decode_lite = on != 0; }
 void tw_debug_set_pdl(int on) { g_pdl = on != 0; }
 
 int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch) {
@@ -1236,7 +1151,7 @@ int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* 
         if (total_ms) *total_ms = tot;
         if (launches) *launches = n;
     }
-    if (bytes_per_launch) *bytes_per_launch = m->prof_bytes;   // K|V bytes of one profiled launch (a sub-batch when the decode is split)
+    if (bytes_per_launch) *bytes_per_launch = m->prof_bytes;   // K|V bytes of one profiled launch
     m->prof_used = 0;
     m->prof_on = enable != 0;
     if (m->prof_on && m->prof_ev.empty()) {

@@ -59,7 +59,7 @@ __device__ __forceinline__ float masked_score(float raw, bool suppressed, int i,
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __restrict__ d_step, RulesDev R, DecodeState S,
+select_tokens_kernel(const float* __restrict__ logits, int64_t ld_logits, int V, const int32_t* __restrict__ d_step, RulesDev R, DecodeState S,
                      int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_lengths, const int32_t* __restrict__ forced,
                      float* __restrict__ logits_tap) {
     __shared__ Best s_text[32], s_ts[32];
@@ -76,7 +76,7 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
     }
     if (gen_index >= out_stride) return;
     if (logits_tap) logits_tap = (gen_index < d_step[STEP_TAP]) ? logits_tap + (int64_t)gen_index * gridDim.x * V : nullptr;
-    const float* row = logits + (int64_t)b * V;
+    const float* row = logits + (int64_t)b * ld_logits;
     const bool ts_mode = R.ts_begin >= 0;
     const int n_hist = S.n_gen[b];
     const bool first = (n_hist == 0);
@@ -182,9 +182,9 @@ select_tokens_kernel(const float* __restrict__ logits, int V, const int32_t* __r
     }
 }
 
-void select_tokens(const float* logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
+void select_tokens(const float* logits, int64_t ld_logits, int V, int B, const int32_t* d_step, const RulesDev& rules, const DecodeState& st,
                    int32_t* out_tokens, int32_t* out_lengths, const int32_t* forced, float* logits_tap, cudaStream_t stream) {
-    launch_k(select_tokens_kernel, dim3(B), dim3(SEL_THREADS), 0, stream, logits, V, d_step, rules, st, out_tokens, out_lengths, forced,
+    launch_k(select_tokens_kernel, dim3(B), dim3(SEL_THREADS), 0, stream, logits, ld_logits, V, d_step, rules, st, out_tokens, out_lengths, forced,
              logits_tap);
 }
 
