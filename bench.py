@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--max-length", type=int, default=MAX_LENGTH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (fp32 check model + HF bf16 comparator)")
+    ap.add_argument("--no-hf-cuda", action="store_true", help="skip the same-box HF bf16/SDPA generate comparator")
+    ap.add_argument("--ref-clips", type=int, default=0, help="--impl reference: clips per step (0 = sized from K + W)")
     return ap.parse_args()
 
 
@@ -157,8 +160,11 @@ def run_reference(args, rank, world):
     sh = SHAPES[args.model]
     model = hf_ref.build_hf_model(sh, seed=1234)
     fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
-    clips_per_step = 1
-    pcm = dequantise(synth_batch(0, clips_per_step * (args.steps + args.warmup)))
+    # a real batch per step (at batch 1 the decoder GEMMs are weight-bandwidth-bound GEMVs, which flatters any ratio taken
+    # against this arm), bounded so that the K + W steps end within minutes on the host cores
+    n_steps = args.steps + args.warmup
+    clips_per_step = args.ref_clips if args.ref_clips > 0 else (8 if n_steps <= 6 else (4 if n_steps <= 12 else 2))
+    pcm = dequantise(synth_batch(0, clips_per_step * n_steps))
 
     def step(i):
         x = pcm[i * clips_per_step:(i + 1) * clips_per_step]
@@ -173,7 +179,8 @@ def run_reference(args, rank, world):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     v = clips_per_step * args.steps * CLIP_SECONDS / dt
-    sample = f"{clips_per_step} clip per step of the {args.batch}-clip batch, full max_length={args.max_length}, fp32"
+    sample = (f"{clips_per_step} clips per step (one HF batch) of the {args.batch}-clip batch, full max_length={args.max_length}, "
+              f"fp32, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "rtfx_audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
@@ -186,8 +193,9 @@ def run_reference(args, rank, world):
     }))
 
 
-def cpu_baseline(args, hf_cpu):
-    """Reference (HF) on the box's host cores, 1 clip, full token budget (~20-40 s of CPU work)."""
+def cpu_baseline(args, hf_cpu, n_clips=2):
+    """Reference (HF) on the box's host cores: one batch of `n_clips` clips, full token budget (~15-30 s of CPU work).
+    Returns (cpu_baseline dict, features [n,n_mel,3000] f32, HF fp32 ids [n, n_gen]) — the ids pin bench parity."""
     import torch
     from oracle import hf_ref
     from taiwan_whisper_b200.configs import SHAPES
@@ -196,14 +204,84 @@ def cpu_baseline(args, hf_cpu):
     torch.set_num_threads(cores)
     sh = SHAPES[args.model]
     fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
-    x = dequantise(synth_batch(0, 1))
+    x = dequantise(synth_batch(0, n_clips))
     t0 = time.perf_counter()
     feats = hf_ref.hf_features(fe, x)
-    hf_ref.hf_generate(hf_cpu, feats, args.max_length, return_timestamps=False)
+    ids = hf_ref.hf_generate(hf_cpu, feats, args.max_length, return_timestamps=False)
     dt = time.perf_counter() - t0
-    return {"value": CLIP_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "reference",
-            "sample": f"1 of the {args.batch} clips, full max_length={args.max_length}, HF transformers fp32 generate + feature "
-                      f"extractor, {dt:.1f} s"}
+    return ({"value": n_clips * CLIP_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+             "sample": f"{n_clips} of the {args.batch} clips as one HF batch, full max_length={args.max_length}, HF transformers fp32 "
+                       f"generate + feature extractor, {dt:.1f} s"}, feats, ids)
+
+
+def parity_block(args, hf_cpu, model, feats, hf_ids, dev):
+    """Parity ON the benched configuration, for the clips the CPU leg decoded with HF fp32:
+      fp32_identical   a full-depth fp32 check-mode instance of this library reproduces HF's ids bit for bit
+      bf16_tf_agree    the benched bf16 model, teacher-forced with HF's ids, picks the same token (all positions)
+      hf_bf16_tf_agree HF's own bf16 forward on this GPU, same positions — the yardstick for bf16_tf_agree"""
+    import numpy as np
+    import torch
+    from oracle import hf_ref
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration
+    from tests.helpers import default_rules
+    sh_vocab = model.shape.vocab
+    prompt = model._init_tokens("zh", "transcribe", False)
+    n, n_gen = hf_ids.shape
+    out = {"n_clips": int(n), "n": int(n * n_gen), "against": "HF transformers fp32 generate on the host CPU, same clips and weights"}
+    ft = torch.from_numpy(feats).to(dev)
+    # fp32 check mode (CUDA-core kernels), full depth, free-running
+    chk = B200WhisperForConditionalGeneration.from_hf(hf_cpu, dtype=torch.float32, max_batch=int(n), device=str(dev), output_layout="5.x")
+    try:
+        enc = chk.encode(ft)
+        toks, lens = chk.decode(enc, prompt, args.max_length, False)
+        toks = toks.cpu().numpy()[:, :n_gen]
+        same = toks == hf_ids
+        out["fp32_identical"] = bool(same.all())
+        out["fp32_first_divergence"] = [int(np.argmin(r)) if not r.all() else None for r in same]
+        ftoks, _ = chk.decode(enc, prompt, args.max_length, False, forced=torch.from_numpy(hf_ids.astype(np.int32)))
+        out["fp32_tf_agree"] = int((ftoks.cpu().numpy()[:, :n_gen] == hf_ids).sum())
+    finally:
+        chk.close()
+    # the benched bf16 instance, teacher-forced on the same ids
+    enc = model.encode(ft)
+    btoks, _ = model.decode(enc, prompt, args.max_length, False, forced=torch.from_numpy(hf_ids.astype(np.int32)))
+    out["bf16_tf_agree"] = int((btoks.cpu().numpy()[:, :n_gen] == hf_ids).sum())
+    hf_b = hf_ref.hf_teacher_forced_argmax(hf_cpu, feats, prompt, hf_ids, default_rules(sh_vocab, False), device=str(dev),
+                                           dtype=torch.bfloat16)
+    out["hf_bf16_tf_agree"] = int((hf_b == hf_ids).sum())
+    out["bf16_tf_frac"] = out["bf16_tf_agree"] / out["n"]
+    out["hf_bf16_tf_frac"] = out["hf_bf16_tf_agree"] / out["n"]
+    return out
+
+
+def hf_cuda_comparator(args, hf_cpu, host_batch, dev):
+    """Same-box GPU comparator ("the library path PyTorch would pick"): the UNMODIFIED HF model in bf16 with
+    SDPA attention, `generate` at the benched batch / max_length on this B200, features precomputed (the reference computes
+    them in CPU dataloader workers).  One warm-up call, one timed call."""
+    import copy
+    import torch
+    from oracle import hf_ref
+    from taiwan_whisper_b200.host import log_mel
+    m = copy.deepcopy(hf_cpu)
+    try:
+        m.set_attn_implementation("sdpa")
+    except Exception:
+        m.config._attn_implementation = "sdpa"
+    m = m.to(device=dev, dtype=torch.bfloat16).eval()
+    feats = log_mel(host_batch.to(dev), None, m.config.num_mel_bins).to(torch.bfloat16)     # input features only; not timed
+    B = feats.shape[0]
+    with torch.no_grad():
+        m.generate(feats[:4], max_length=16, num_beams=1, return_timestamps=False, language="zh", task="transcribe")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids = m.generate(feats, max_length=args.max_length, num_beams=1, return_timestamps=False, language="zh", task="transcribe")
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    del m
+    torch.cuda.empty_cache()
+    return {"hf_cuda_rtfx": B * CLIP_SECONDS / dt, "hf_cuda_s_per_batch": dt, "hf_cuda_tokens": int(ids.shape[1]),
+            "hf_cuda_config": f"transformers {__import__('transformers').__version__} WhisperForConditionalGeneration.generate, bf16, "
+                              f"attn_implementation=sdpa, batch {B}, max_length {args.max_length}, features precomputed, 1 timed call"}
 
 
 def main():
@@ -234,7 +312,7 @@ def main():
     # random-init weights of the architecture (HF init), built directly on the GPU
     with torch.device(dev):
         hf = build_hf_model(sh, seed=1234)
-    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev))
+    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev), output_layout="5.x")
     hf_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is reported at N=1 only
         hf_cpu = hf.to("cpu")
@@ -381,7 +459,18 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "stages": stages,
         }
         if hf_cpu is not None:
-            line["cpu_baseline"] = cpu_baseline(args, hf_cpu)
+            cb, ref_feats, ref_ids = cpu_baseline(args, hf_cpu)
+            line["cpu_baseline"] = cb
+            if not args.no_parity:
+                try:
+                    line["parity"] = parity_block(args, hf_cpu, model, ref_feats, ref_ids, dev)
+                except Exception as e:        # the throughput line must survive a parity-leg failure; the failure is reported
+                    line["parity"] = {"error": f"{type(e).__name__}: {e}"}
+            if not args.no_hf_cuda:
+                try:
+                    line["extra"] = hf_cuda_comparator(args, hf_cpu, host_batches[0], dev)
+                except Exception as e:
+                    line["extra"] = {"hf_cuda_error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -101,6 +101,9 @@ TW_API int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight
 TW_API void tw_model_free(tw_model* m);
 /* bytes of device memory the model holds for weights + workspace at max_batch */
 TW_API size_t tw_model_bytes(const tw_model* m);
+/* the descriptor the model was loaded with (what a caller that only holds the handle needs to size its buffers:
+ * torch.ops.twb200.* take the tw_model* as an int64, see taiwan-whisper_b200/host.py) */
+TW_API int tw_model_get_desc(const tw_model* m, tw_model_desc* out);
 /* Device bytes tw_model_load would allocate for this descriptor (repacked weights, workspace, cross-attention K|V store,
  * paged self-attention pools) — host arithmetic only, usable for sizing max_batch against the 180 GB of a B200 before loading. */
 TW_API size_t tw_workspace_bytes(const tw_model_desc* desc);

@@ -54,3 +54,28 @@ def hf_encoder_states(model, feats: np.ndarray):
     enc = model.model.encoder
     out = enc(torch.as_tensor(feats), output_hidden_states=True, return_dict=True)
     return [h.numpy() for h in out.hidden_states], out.last_hidden_state.numpy()
+
+
+@torch.no_grad()
+def hf_teacher_forced_argmax(model, feats, prompt, forced, rules, device="cpu", dtype=torch.float32):
+    """The reference implementation's per-position greedy choice when it is fed a given token history: one HF forward
+    (`model(input_features, decoder_input_ids).logits`, modeling_whisper.py:1000-1100) over [prompt + forced[:-1]] at `dtype` on
+    `device`, then the logits rules (oracle apply_rules = HF's processors) and argmax at every generated position.
+    feats [n, n_mel, 3000] f32, forced [n, n_gen] int.  Returns int64 [n, n_gen].  This is how "HF's own bf16" is scored
+    against the fp32 token stream on the same positions."""
+    import copy
+
+    from oracle import whisper_np
+    forced = np.asarray(forced)
+    n, n_gen = forced.shape
+    P = len(prompt)
+    m = copy.deepcopy(model).to(device=device, dtype=dtype).eval()
+    dec_in = np.concatenate([np.tile(np.asarray(prompt)[None], (n, 1)), forced[:, :-1]], axis=1)
+    out = np.zeros((n, n_gen), dtype=np.int64)
+    for i in range(n):                      # row by row: bounded memory for [T, V] fp32 logits
+        lg = m(input_features=torch.as_tensor(feats[i:i + 1]).to(device=device, dtype=dtype),
+               decoder_input_ids=torch.as_tensor(dec_in[i:i + 1]).to(device)).logits[0, P - 1:].float().cpu().numpy()
+        for s in range(n_gen):
+            out[i, s] = int(np.argmax(whisper_np.apply_rules(lg[s], forced[i, :s].tolist(), rules)))
+    del m
+    return out

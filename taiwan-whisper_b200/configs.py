@@ -63,6 +63,10 @@ SHAPES = {
     # test-only miniatures (same code paths, seconds on CPU)
     "micro80": WhisperShape("micro80", 80, 128, 256, 2, 2, 2, 51865),
     "micro128": WhisperShape("micro128", 128, 128, 512, 2, 2, 2, 51866),
+    # test-only: the benched widths with few layers — large-v3 (configs[1]) and medium (configs[4]) at full d / heads / ffn /
+    # vocabulary / mel bins, so that the parity tests run the kernels at the tile shapes the bench uses
+    "lv3w": WhisperShape("lv3w", 128, 1280, 5120, 20, 2, 2, 51866),
+    "medw": WhisperShape("medw", 80, 1024, 4096, 16, 2, 2, 51865),
 }
 
 

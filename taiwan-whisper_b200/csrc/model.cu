@@ -867,6 +867,12 @@ void tw_model_free(tw_model* m) {
 
 size_t tw_model_bytes(const tw_model* m) { return m ? m->bytes : 0; }
 
+int tw_model_get_desc(const tw_model* m, tw_model_desc* out) {
+    if (!m || !out) return TW_E_INVALID;
+    *out = m->desc;
+    return TW_OK;
+}
+
 size_t tw_workspace_bytes(const tw_model_desc* desc) {
     // Device bytes tw_model_load will allocate for this descriptor (repacked weights + workspace + K|V stores), without
     // touching a device: the same expressions as load_weights / alloc_workspace (a -m gpu test pins the two together).

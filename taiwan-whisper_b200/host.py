@@ -60,53 +60,184 @@ def log_mel(pcm: torch.Tensor, n_valid: Optional[torch.Tensor], n_mel: int) -> t
     return out
 
 
+_DESC_FIELDS = ("d_model", "ffn", "heads", "enc_layers", "dec_layers", "n_mel", "vocab", "max_target", "dtype", "max_batch")
+_TW2TORCH = {_lib.TW_F32: torch.float32, _lib.TW_BF16: torch.bfloat16}
+
+
+def model_desc(handle: int) -> "_lib.ModelDesc":
+    """The descriptor behind a raw `tw_model*` (int): everything the functional layer needs to size its outputs."""
+    d = _lib.ModelDesc()
+    rc = _lib.load_library().tw_model_get_desc(C.c_void_p(handle), C.byref(d))
+    if rc != _lib.TW_OK:
+        raise ValueError("twb200: not a live model handle")
+    return d
+
+
+def model_create(desc: Sequence[int], names: Sequence[str], weights: Sequence[torch.Tensor]) -> int:
+    """tw_model_load over CUDA tensors: desc = (d_model, ffn, heads, enc_layers, dec_layers, n_mel, vocab, max_target,
+    dtype, max_batch), names = HF state_dict keys.  Returns the `tw_model*` as an int — the handle every other op takes;
+    the model owns repacked copies, so the weight tensors may be freed afterwards.  Release with model_free()."""
+    if len(desc) != len(_DESC_FIELDS) or len(names) != len(weights) or not weights:
+        raise ValueError("model_create: desc needs 10 ints and one name per weight tensor")
+    dev = _dev_index(weights[0].device)
+    ctx = _lib.Context.get(dev)
+    keep, table = [], []
+    with torch.cuda.device(dev):
+        for name, t in zip(names, weights):
+            t = t.detach()
+            if t.dtype not in (torch.float32, torch.bfloat16):
+                t = t.float()
+            t = t.to(f"cuda:{dev}").contiguous()
+            keep.append(t)
+            table.append(_lib.Weight(name.encode(), t.data_ptr(), _TORCH2TW[t.dtype], t.numel()))
+        torch.cuda.synchronize(dev)
+        arr = (_lib.Weight * len(table))(*table)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.tw_model_load(ctx.handle, C.byref(_lib.ModelDesc(*[int(v) for v in desc])), arr, len(table), C.byref(h)))
+    del keep
+    return int(h.value)
+
+
+def model_free(handle: int) -> None:
+    _lib.load_library().tw_model_free(C.c_void_p(handle))
+
+
+def encoder_forward(handle: int, mel: torch.Tensor, tap_layer: int = -1):
+    """mel [B, n_mel, 3000] float32 cuda -> enc_out [B, 1500, d] in the model dtype (tw_encode); with tap_layer >= 0 also
+    the fp32 residual stream after that many layers."""
+    d = model_desc(handle)
+    if mel.dim() != 3 or mel.shape[-1] != N_FRAMES or mel.shape[-2] != d.n_mel:
+        # HF raises ValueError on a wrong feature length (modeling_whisper.py:613-617)
+        raise ValueError(f"Whisper expects the mel input features to be of length {N_FRAMES}, but found "
+                         f"{mel.shape[-1]}. Make sure to pad the input mel features to {N_FRAMES}.")
+    dev = _dev_index(mel.device)
+    ctx = _lib.Context.get(dev)
+    mel = mel.to(torch.float32).contiguous()
+    B = mel.shape[0]
+    out = torch.empty((B, 1500, d.d_model), dtype=_TW2TORCH[d.dtype], device=mel.device)
+    tap = torch.empty((B, 1500, d.d_model), dtype=torch.float32, device=mel.device) if tap_layer >= 0 else None
+    with torch.cuda.device(dev):
+        ctx.check(ctx.lib.tw_encode(C.c_void_p(handle), mel.data_ptr(), B, out.data_ptr(), tap_layer,
+                                    tap.data_ptr() if tap is not None else None, _stream_ptr(mel.device)))
+    return (out, tap) if tap_layer >= 0 else out
+
+
+def greedy_decode(handle: int, enc_out: torch.Tensor, prompt: Sequence[int], max_length: int, suppress: Sequence[int],
+                  begin_suppress: Sequence[int], eos: int, pad: int, timestamp_begin: int, no_timestamps: int,
+                  max_initial_ts: int, forced: Optional[torch.Tensor] = None, tap_steps: int = 0):
+    """enc_out [B, 1500, d] (cuda, model dtype) -> (tokens int32 [B, max_length - P], lengths int32 [B]) by tw_decode_greedy.
+    timestamp_begin < 0 switches the timestamp rules off; max_initial_ts < 0 = no limit.  forced / tap_steps: teacher
+    forcing and post-rules logits taps for the parity tests."""
+    d = model_desc(handle)
+    B = enc_out.shape[0]
+    n_gen = max_length - len(prompt)
+    if n_gen <= 0 or max_length > d.max_target:
+        raise ValueError(f"The length of the prompt ({len(prompt)}) plus the new tokens must fit max_length "
+                         f"<= max_target_positions ({d.max_target}); got max_length={max_length}")
+    dev = _dev_index(enc_out.device)
+    ctx = _lib.Context.get(dev)
+    enc_out = enc_out.to(_TW2TORCH[d.dtype]).contiguous()
+    toks = torch.empty((B, n_gen), dtype=torch.int32, device=enc_out.device)
+    lens = torch.empty((B,), dtype=torch.int32, device=enc_out.device)
+    tap = torch.empty((tap_steps, B, d.vocab), dtype=torch.float32, device=enc_out.device) if tap_steps else None
+    if forced is not None:
+        forced = forced.to(enc_out.device, torch.int32).contiguous()
+        assert forced.shape == (B, n_gen)
+    rules, keep = _lib.make_rules(list(suppress), list(begin_suppress), int(eos), int(pad),
+                                  None if timestamp_begin is None or timestamp_begin < 0 else int(timestamp_begin),
+                                  int(no_timestamps), None if max_initial_ts is None or max_initial_ts < 0 else int(max_initial_ts))
+    p = (C.c_int32 * len(prompt))(*[int(t) for t in prompt])
+    with torch.cuda.device(dev):
+        ctx.check(ctx.lib.tw_decode_greedy(
+            C.c_void_p(handle), enc_out.data_ptr(), B, p, len(prompt), C.byref(rules), max_length, toks.data_ptr(),
+            lens.data_ptr(), forced.data_ptr() if forced is not None else None,
+            tap.data_ptr() if tap is not None else None, tap_steps, _stream_ptr(enc_out.device)))
+    del keep
+    return (toks, lens, tap) if tap_steps else (toks, lens)
+
+
+def decoder_logits(handle: int, enc_out: torch.Tensor, decoder_input_ids: torch.Tensor) -> torch.Tensor:
+    """enc_out [B,1500,d] + decoder_input_ids [B,T] -> fp32 logits [B,T,V] of every position in ONE batched decoder pass
+    (tw_decoder_logits).  The returned tensor is a view whose row pitch is V rounded up to 4 floats."""
+    d = model_desc(handle)
+    if decoder_input_ids.dim() != 2:
+        raise ValueError("decoder_input_ids must be [batch, target_length]")
+    B, T = decoder_input_ids.shape
+    if B > d.max_batch:
+        raise ValueError(f"batch {B} > max_batch {d.max_batch}")
+    if T < 1 or T > d.max_target:
+        raise ValueError(f"decoder_input_ids length {T} must be in 1..max_target_positions ({d.max_target})")
+    dev = _dev_index(enc_out.device)
+    ctx = _lib.Context.get(dev)
+    enc_out = enc_out.to(_TW2TORCH[d.dtype]).contiguous()
+    if enc_out.shape != (B, 1500, d.d_model):
+        raise ValueError(f"encoder output must be [{B}, 1500, {d.d_model}], got {tuple(enc_out.shape)}")
+    ids = decoder_input_ids.to(enc_out.device, torch.int32).contiguous()
+    V = d.vocab
+    ld = (V + 3) // 4 * 4
+    buf = torch.empty((B * T, ld), dtype=torch.float32, device=enc_out.device)
+    with torch.cuda.device(dev):
+        ctx.check(ctx.lib.tw_decoder_logits(C.c_void_p(handle), enc_out.data_ptr(), B, ids.data_ptr(), T, buf.data_ptr(), ld,
+                                            _stream_ptr(enc_out.device)))
+    return buf.view(B, T, ld)[:, :, :V]
+
+
 def _register_torch_ops():
-    """torch.ops.twb200.{log_mel, encoder_forward, greedy_generate, decoder_logits}: thin operator wrappers over the
-    C ABI (CUDA tensors only, current stream)."""
+    """torch.ops.twb200.{log_mel, model_create, model_free, encoder_forward, greedy_generate, decoder_logits}: operator
+    wrappers over the C ABI (CUDA tensors only, current stream).  A model is addressed by its `tw_model*` passed as an int —
+    the value model_create returns — so the ops need no Python-side object."""
     try:
         from torch.library import custom_op
     except Exception:  # pragma: no cover
         return
 
     @custom_op("twb200::log_mel", mutates_args=())
-    def _op_log_mel(pcm: torch.Tensor, n_mel: int) -> torch.Tensor:
-        return log_mel(pcm, None, n_mel)
+    def _op_log_mel(pcm: torch.Tensor, n_valid: Optional[torch.Tensor], n_mel: int) -> torch.Tensor:
+        return log_mel(pcm, n_valid, n_mel)
 
     @_op_log_mel.register_fake
-    def _(pcm, n_mel):
+    def _(pcm, n_valid, n_mel):
         return pcm.new_empty((pcm.shape[0], n_mel, N_FRAMES), dtype=torch.float32)
+
+    @custom_op("twb200::model_create", mutates_args=())
+    def _op_model_create(desc: Sequence[int], names: str, weights: Sequence[torch.Tensor]) -> int:
+        return model_create(list(desc), names.split("\n"), list(weights))
+
+    @custom_op("twb200::model_free", mutates_args=())
+    def _op_model_free(handle: int) -> None:
+        model_free(handle)
 
     @custom_op("twb200::encoder_forward", mutates_args=())
     def _op_encoder_forward(handle: int, mel: torch.Tensor) -> torch.Tensor:
-        return _MODELS[handle].encode(mel)
+        return encoder_forward(handle, mel)
 
     @_op_encoder_forward.register_fake
     def _(handle, mel):
-        m = _MODELS[handle]
-        return mel.new_empty((mel.shape[0], 1500, m.shape.d_model), dtype=m.dtype)
+        d = model_desc(handle)
+        return mel.new_empty((mel.shape[0], 1500, d.d_model), dtype=_TW2TORCH[d.dtype])
 
     @custom_op("twb200::greedy_generate", mutates_args=())
-    def _op_greedy_generate(handle: int, enc_out: torch.Tensor, prompt: Sequence[int], max_length: int,
-                            timestamps: bool) -> torch.Tensor:
-        toks, lens = _MODELS[handle].decode(enc_out, list(prompt), max_length, timestamps)
+    def _op_greedy_generate(handle: int, enc_out: torch.Tensor, prompt: Sequence[int], max_length: int, suppress: Sequence[int],
+                            begin_suppress: Sequence[int], eos: int, pad: int, timestamp_begin: int, no_timestamps: int,
+                            max_initial_ts: int) -> torch.Tensor:
+        # [B, max_length - P + 1] int32: the generated ids, then the row's length in the last column
+        toks, lens = greedy_decode(handle, enc_out, list(prompt), max_length, list(suppress), list(begin_suppress), eos, pad,
+                                   timestamp_begin, no_timestamps, max_initial_ts)
         return torch.cat([toks, lens[:, None]], dim=1)
 
     @_op_greedy_generate.register_fake
-    def _(handle, enc_out, prompt, max_length, timestamps):
+    def _(handle, enc_out, prompt, max_length, suppress, begin_suppress, eos, pad, timestamp_begin, no_timestamps, max_initial_ts):
         return enc_out.new_empty((enc_out.shape[0], max_length - len(prompt) + 1), dtype=torch.int32)
 
     @custom_op("twb200::decoder_logits", mutates_args=())
     def _op_decoder_logits(handle: int, enc_out: torch.Tensor, decoder_input_ids: torch.Tensor) -> torch.Tensor:
         # the custom-op contract wants an owning tensor: copy the pitched view into a dense [B, T, V]
-        return _MODELS[handle].decoder_logits(enc_out, decoder_input_ids).contiguous()
+        return decoder_logits(handle, enc_out, decoder_input_ids).contiguous()
 
     @_op_decoder_logits.register_fake
     def _(handle, enc_out, decoder_input_ids):
-        m = _MODELS[handle]
-        return enc_out.new_empty((decoder_input_ids.shape[0], decoder_input_ids.shape[1], m.shape.vocab), dtype=torch.float32)
-
-
-_MODELS: dict = {}
+        d = model_desc(handle)
+        return enc_out.new_empty((decoder_input_ids.shape[0], decoder_input_ids.shape[1], d.vocab), dtype=torch.float32)
 
 
 # --------------------------------------------------------------------------------------------
@@ -123,6 +254,17 @@ class BatchFeature(dict):
         return BatchFeature({k: (v.to(*a, **kw) if torch.is_tensor(v) else v) for k, v in self.items()})
 
 
+class DeviceFeatureList(list):
+    """What `fe(..., return_tensors=None)` returns as `input_features` when the extractor was built with
+    `keep_on_device=True`: a list of per-clip CUDA tensors (views of one [B, n_mel, 3000] batch tensor, kept in `.batch`).
+    The only thing the reference does with that list is hand it to `fe.pad(...)` (ref prefiltering/validator_inference.py:
+    57-69), which returns `.batch` itself — the features never visit the host."""
+
+    def __init__(self, batch: torch.Tensor):
+        super().__init__(batch.unbind(0))
+        self.batch = batch
+
+
 class B200WhisperFeatureExtractor:
     """Drop-in for WhisperFeatureExtractor on the reference's call sites
     (ref: training/run_pseudo_labelling.py:739-741; prefiltering/validator_inference.py:57-69).
@@ -131,7 +273,8 @@ class B200WhisperFeatureExtractor:
     model_input_names = ["input_features"]
 
     def __init__(self, feature_size: int = 80, sampling_rate: int = SAMPLING_RATE, hop_length: int = 160,
-                 chunk_length: int = 30, n_fft: int = 400, padding_value: float = 0.0, device: str = "cuda", **kwargs):
+                 chunk_length: int = 30, n_fft: int = 400, padding_value: float = 0.0, device: str = "cuda",
+                 keep_on_device: bool = False, **kwargs):
         if (sampling_rate, hop_length, chunk_length, n_fft) != (16000, 160, 30, 400):
             raise NotImplementedError("the B200 log-mel kernel is specialised for 16 kHz / n_fft 400 / hop 160 / 30 s")
         if feature_size not in (80, 128):
@@ -145,6 +288,9 @@ class B200WhisperFeatureExtractor:
         self.nb_max_frames = N_FRAMES
         self.padding_value = padding_value
         self.device = device
+        # return_tensors=None normally yields host numpy arrays (what `datasets.map` stores, ref run_pseudo_labelling.py:
+        # 739-741); with keep_on_device the list holds CUDA views and `pad` hands the batch tensor straight to generate
+        self.keep_on_device = keep_on_device
 
     @classmethod
     def from_hf(cls, hf_fe, device: str = "cuda"):
@@ -166,6 +312,8 @@ class B200WhisperFeatureExtractor:
         feats = log_mel(pcm, n_valid, self.feature_size)
         if return_tensors == "pt":
             out = feats
+        elif return_tensors is None and self.keep_on_device:
+            out = DeviceFeatureList(feats)
         elif return_tensors in (None, "np"):
             arr = feats.cpu().numpy()
             out = arr if return_tensors == "np" else [a for a in arr]
@@ -211,12 +359,16 @@ class B200WhisperFeatureExtractor:
         every window is already 3000 frames long, so this only stacks."""
         feats = processed_features["input_features"] if isinstance(processed_features, dict) else \
             [f["input_features"] for f in processed_features]
-        if torch.is_tensor(feats):
+        if isinstance(feats, DeviceFeatureList):
+            stacked = feats.batch
+        elif torch.is_tensor(feats):
             stacked = feats
         else:
             stacked = torch.stack([torch.as_tensor(f) for f in feats])
         if return_tensors in (None, "np"):
             stacked = stacked.cpu().numpy()
+        elif return_tensors != "pt":
+            raise ValueError(f"unsupported return_tensors={return_tensors!r}")
         return BatchFeature({"input_features": stacked})
 
 
@@ -256,7 +408,17 @@ class B200WhisperForConditionalGeneration:
     """Drop-in for the `WhisperForConditionalGeneration` object the reference scripts hold, on the
     surface they touch: .eval(), .to(), .config, .generation_config, .generate(...), .module."""
 
-    def __init__(self, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda"):
+    def __init__(self, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda",
+                 output_layout: str = "4.45"):
+        """output_layout: which transformers release `generate()` imitates where the releases differ.
+        "4.45" (default; the reference pins transformers==4.45.2, ref environment.yml:175): ids start with the forced
+        prompt `<|sot|><|lang|><|task|>[<|notimestamps|>]` — the layout ref run_pseudo_labelling.py:629,1009-1010
+        slices with `timestamp_position` — and a <= 30 s window is decoded exactly once with return_timestamps=True.
+        "5.x" (the transformers installed in this image, which pins the oracle): generated ids only, and
+        return_timestamps=True runs the seek loop.  `return_prompt=` / `seek_loop=` override either per call."""
+        if output_layout not in ("4.45", "5.x"):
+            raise ValueError('output_layout must be "4.45" (the reference\'s pinned transformers) or "5.x"')
+        self.output_layout = output_layout
         cfg = hf_model.config
         self.config = cfg
         self.generation_config = hf_model.generation_config
@@ -271,35 +433,20 @@ class B200WhisperForConditionalGeneration:
         self.shape = WhisperShape("hf", cfg.num_mel_bins, cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_attention_heads,
                                   cfg.encoder_layers, cfg.decoder_layers, cfg.vocab_size, cfg.max_target_positions)
         self.max_batch = max_batch
-        desc = _lib.ModelDesc(cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_attention_heads, cfg.encoder_layers,
-                              cfg.decoder_layers, cfg.num_mel_bins, cfg.vocab_size, cfg.max_target_positions,
-                              _TORCH2TW[dtype], max_batch)
-        # weights snapshot (after any embedding surgery such as utils/model_utils.py:4-14) -> device
-        sd = hf_model.state_dict()
-        keep, table = [], []
+        desc = (cfg.d_model, cfg.encoder_ffn_dim, cfg.encoder_attention_heads, cfg.encoder_layers, cfg.decoder_layers,
+                cfg.num_mel_bins, cfg.vocab_size, cfg.max_target_positions, _TORCH2TW[dtype], max_batch)
+        # weights snapshot (after any embedding surgery such as utils/model_utils.py:4-14) -> device; proj_out.weight is
+        # tied to embed_tokens, so only the "model." tensors are passed
+        sd = {k: v for k, v in hf_model.state_dict().items() if k.startswith("model.")}
         with torch.cuda.device(self.device):
-            for name, t in sd.items():
-                if not name.startswith("model."):
-                    continue                      # proj_out.weight is tied to embed_tokens
-                t = t.detach()
-                if t.dtype not in (torch.float32, torch.bfloat16):
-                    t = t.float()
-                t = t.to(self.device).contiguous()
-                keep.append(t)
-                table.append(_lib.Weight(name.encode(), t.data_ptr(), _TORCH2TW[t.dtype], t.numel()))
-            torch.cuda.synchronize(self.device)
-            arr = (_lib.Weight * len(table))(*table)
-            h = C.c_void_p()
-            self.ctx.check(self.ctx.lib.tw_model_load(self.ctx.handle, C.byref(desc), arr, len(table), C.byref(h)))
-        self.handle = h
-        del keep
-        self._id = id(self)
-        _MODELS[self._id] = self
+            weights = [t.detach().to(self.device) for t in sd.values()]
+            self.handle = model_create(desc, list(sd.keys()), weights)       # the tw_model* as an int (torch.ops take it as is)
+        del weights
         self.training = False
 
     @classmethod
-    def from_hf(cls, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda"):
-        return cls(hf_model, dtype=dtype, max_batch=max_batch, device=device)
+    def from_hf(cls, hf_model, dtype=torch.bfloat16, max_batch: int = 64, device: str = "cuda", output_layout: str = "4.45"):
+        return cls(hf_model, dtype=dtype, max_batch=max_batch, device=device, output_layout=output_layout)
 
     # ---- nn.Module-ish surface the scripts touch
     def eval(self):
@@ -317,9 +464,8 @@ class B200WhisperForConditionalGeneration:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.ctx.lib.tw_model_free(self.handle)
+            model_free(self.handle)
             self.handle = None
-            _MODELS.pop(self._id, None)
 
     def __del__(self):
         try:
@@ -328,7 +474,7 @@ class B200WhisperForConditionalGeneration:
             pass
 
     def device_bytes(self) -> int:
-        return int(self.ctx.lib.tw_model_bytes(self.handle))
+        return int(self.ctx.lib.tw_model_bytes(C.c_void_p(self.handle)))
 
     # ---- generation config plumbing (generation_whisper.py:1455-1608, :1774-1812)
     def _init_tokens(self, language, task, return_timestamps):
@@ -342,7 +488,12 @@ class B200WhisperForConditionalGeneration:
             if language is not None or task is not None:
                 raise ValueError("Cannot specify `task` or `language` for an English-only model.")
         else:
-            lang = "en" if language is None else str(language).lower()
+            if language is None:
+                # HF runs language detection here (generation_whisper.py:1530-1560); the reference always forwards
+                # data_args.language / 'zh'.  Guessing a language would silently mislabel a corpus.
+                raise NotImplementedError("language=None on a multilingual checkpoint needs language detection, which the "
+                                          "B200 path does not implement: pass language='zh' (or another code) explicitly")
+            lang = str(language).lower()
             if lang in gc.lang_to_id:
                 lang_tok = lang
             elif f"<|{lang}|>" in gc.lang_to_id:
@@ -374,68 +525,20 @@ class B200WhisperForConditionalGeneration:
 
     # ---- device-level entry points
     def encode(self, mel: torch.Tensor, tap_layer: int = -1):
-        """mel [B, n_mel, 3000] float32 cuda -> enc_out [B,1500,d] (model dtype); with tap_layer >= 0 also
+        """mel [B, n_mel, 3000] float32 -> enc_out [B,1500,d] (model dtype, on the model's device); with tap_layer >= 0 also
         returns the fp32 residual stream after that many layers."""
-        if mel.shape[-1] != N_FRAMES or mel.shape[-2] != self.shape.n_mel:
-            # HF raises ValueError on a wrong feature length (modeling_whisper.py:613-617)
-            raise ValueError(f"Whisper expects the mel input features to be of length {N_FRAMES}, but found "
-                             f"{mel.shape[-1]}. Make sure to pad the input mel features to {N_FRAMES}.")
-        mel = mel.to(self.device, torch.float32).contiguous()
-        B = mel.shape[0]
-        out = torch.empty((B, 1500, self.shape.d_model), dtype=self.dtype, device=self.device)
-        tap = torch.empty((B, 1500, self.shape.d_model), dtype=torch.float32, device=self.device) if tap_layer >= 0 else None
-        with torch.cuda.device(self.device):
-            self.ctx.check(self.ctx.lib.tw_encode(self.handle, mel.data_ptr(), B, out.data_ptr(), tap_layer,
-                                                  tap.data_ptr() if tap is not None else None, _stream_ptr(self.device)))
-        return (out, tap) if tap_layer >= 0 else out
+        return encoder_forward(self.handle, torch.as_tensor(mel).to(self.device), tap_layer)
 
     def decode(self, enc_out: torch.Tensor, prompt, max_length: int, timestamps: bool, forced: Optional[torch.Tensor] = None,
                tap_steps: int = 0):
-        B = enc_out.shape[0]
-        n_gen = max_length - len(prompt)
-        if n_gen <= 0 or max_length > self.shape.max_target:
-            raise ValueError(f"The length of the prompt ({len(prompt)}) plus the new tokens must fit max_length "
-                             f"<= max_target_positions ({self.shape.max_target}); got max_length={max_length}")
-        enc_out = enc_out.to(self.device, self.dtype).contiguous()
-        toks = torch.empty((B, n_gen), dtype=torch.int32, device=self.device)
-        lens = torch.empty((B,), dtype=torch.int32, device=self.device)
-        tap = torch.empty((tap_steps, B, self.shape.vocab), dtype=torch.float32, device=self.device) if tap_steps else None
-        if forced is not None:
-            forced = forced.to(self.device, torch.int32).contiguous()
-            assert forced.shape == (B, n_gen)
         r = self._rules(timestamps)
-        rules, keep = _lib.make_rules(r["suppress"], r["begin_suppress"], r["eos"], r["pad"], r["timestamp_begin"],
-                                      r["no_timestamps"], r["max_initial_ts"])
-        p = (C.c_int32 * len(prompt))(*prompt)
-        with torch.cuda.device(self.device):
-            self.ctx.check(self.ctx.lib.tw_decode_greedy(
-                self.handle, enc_out.data_ptr(), B, p, len(prompt), C.byref(rules), max_length, toks.data_ptr(),
-                lens.data_ptr(), forced.data_ptr() if forced is not None else None,
-                tap.data_ptr() if tap is not None else None, tap_steps, _stream_ptr(self.device)))
-        del keep
-        return (toks, lens, tap) if tap_steps else (toks, lens)
+        return greedy_decode(self.handle, enc_out.to(self.device), list(prompt), max_length, r["suppress"], r["begin_suppress"],
+                             r["eos"], r["pad"], -1 if r["timestamp_begin"] is None else r["timestamp_begin"], r["no_timestamps"],
+                             -1 if r["max_initial_ts"] is None else r["max_initial_ts"], forced=forced, tap_steps=tap_steps)
 
     def decoder_logits(self, enc_out: torch.Tensor, decoder_input_ids: torch.Tensor) -> torch.Tensor:
-        """enc_out [B,1500,d] + decoder_input_ids [B,T] -> fp32 logits [B,T,V] of every position in ONE batched decoder pass
-        (tw_decoder_logits).  The returned tensor is a view whose row pitch is V rounded up to 4 floats."""
-        if decoder_input_ids.dim() != 2:
-            raise ValueError("decoder_input_ids must be [batch, target_length]")
-        B, T = decoder_input_ids.shape
-        if B > self.max_batch:
-            raise ValueError(f"batch {B} > max_batch {self.max_batch}")
-        if T < 1 or T > self.shape.max_target:
-            raise ValueError(f"decoder_input_ids length {T} must be in 1..max_target_positions ({self.shape.max_target})")
-        enc_out = enc_out.to(self.device, self.dtype).contiguous()
-        if enc_out.shape != (B, 1500, self.shape.d_model):
-            raise ValueError(f"encoder output must be [{B}, 1500, {self.shape.d_model}], got {tuple(enc_out.shape)}")
-        ids = decoder_input_ids.to(self.device, torch.int32).contiguous()
-        V = self.shape.vocab
-        ld = (V + 3) // 4 * 4
-        buf = torch.empty((B * T, ld), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            self.ctx.check(self.ctx.lib.tw_decoder_logits(self.handle, enc_out.data_ptr(), B, ids.data_ptr(), T, buf.data_ptr(), ld,
-                                                          _stream_ptr(self.device)))
-        return buf.view(B, T, ld)[:, :, :V]
+        """enc_out [B,1500,d] + decoder_input_ids [B,T] -> fp32 logits [B,T,V] of every position in ONE batched decoder pass."""
+        return decoder_logits(self.handle, enc_out.to(self.device), decoder_input_ids)
 
     def shift_tokens_right(self, labels: torch.Tensor) -> torch.Tensor:
         """HF shift_tokens_right (modeling_whisper.py:67-81): prepend decoder_start_token_id, drop the last label, -100 -> pad."""
@@ -501,7 +604,7 @@ class B200WhisperForConditionalGeneration:
         nv = n_valid.contiguous().data_ptr() if n_valid is not None else None
         with torch.cuda.device(self.device):
             self.ctx.check(self.ctx.lib.tw_transcribe_host(
-                self.handle, pcm_host.data_ptr(), nv, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
+                C.c_void_p(self.handle), pcm_host.data_ptr(), nv, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
                 out_lengths.data_ptr(), _stream_ptr(self.device)))
         del keep
         return out_tokens, out_lengths
@@ -511,29 +614,33 @@ class B200WhisperForConditionalGeneration:
         Returns (total_ms, launches); `last_profile_bytes` holds the K|V bytes of one sampled launch (one sub-batch
         of the batch when the decode step is split)."""
         ms, n, nb = C.c_float(0), C.c_int(0), C.c_double(0)
-        self.ctx.check(self.ctx.lib.tw_profile(self.handle, 1 if enable else 0, C.byref(ms), C.byref(n), C.byref(nb)))
+        self.ctx.check(self.ctx.lib.tw_profile(C.c_void_p(self.handle), 1 if enable else 0, C.byref(ms), C.byref(n), C.byref(nb)))
         self.last_profile_bytes = float(nb.value)
         return float(ms.value), int(n.value)
 
     def last_stage_ms(self):
         buf = (C.c_float * 6)()
-        self.ctx.lib.tw_last_stage_ms(self.handle, buf)
+        self.ctx.lib.tw_last_stage_ms(C.c_void_p(self.handle), buf)
         return dict(zip(("logmel", "encoder", "cross_kv", "decode", "total", "h2d"), [float(x) for x in buf]))
 
     # ---- the reference's call
     @torch.no_grad()
     def generate(self, input_features=None, *, max_length: Optional[int] = None, max_new_tokens: Optional[int] = None,
                  num_beams: int = 1, return_timestamps: Optional[bool] = None, language: Optional[str] = None,
-                 task: Optional[str] = None, attention_mask=None, return_prompt: bool = False, seek_loop: bool = True,
-                 **kwargs):
+                 task: Optional[str] = None, attention_mask=None, return_prompt: Optional[bool] = None,
+                 seek_loop: Optional[bool] = None, **kwargs):
         """ref: training/run_pseudo_labelling.py:864-876,917-918; prefiltering/validator_inference.py:41-47,78.
-        Returns a LongTensor [B, L] of generated ids (after the forced prompt, as transformers >= 4.46 / 5.x
-        return them; `return_prompt=True` prepends the prompt, the 4.45 layout ref :629,1009-1010 expects),
-        EOS stripped, right-padded with pad_token_id to the batch maximum.  One 30 s window per row.
-        With return_timestamps=True and seek_loop=True (default) the host runs the installed transformers' (5.x)
-        seek loop around the window primitive: split at consecutive timestamp tokens, advance to the last predicted
-        timestamp, re-encode the zero-padded remainder (generation_whisper.py:785-900, 1976-2073); seek_loop=False
-        decodes each window exactly once (the short-form behaviour of the 4.45 the reference pins)."""
+        Returns a LongTensor [B, L], EOS stripped, right-padded with pad_token_id to the batch maximum; one 30 s window
+        per row.  `return_prompt` (default: True under output_layout "4.45", False under "5.x"): whether the forced prompt
+        leads every row — the reference's `add_concatenated_text` (ref :1003-1012) drops `timestamp_position` = 3 leading
+        ids and therefore needs it.  `seek_loop` (default: False under "4.45", True under "5.x"): with
+        return_timestamps=True, run the 5.x seek loop around the window primitive — split at consecutive timestamp
+        tokens, advance to the last predicted timestamp, re-encode the zero-padded remainder (generation_whisper.py:
+        785-900, 1976-2073) — or decode each window exactly once (short-form behaviour of 4.45)."""
+        if return_prompt is None:
+            return_prompt = self.output_layout == "4.45"
+        if seek_loop is None:
+            seek_loop = self.output_layout == "5.x"
         if num_beams not in (None, 1):
             raise NotImplementedError("twb200 implements greedy decoding only (num_beams=1), as the reference's "
                                       "pseudo-labelling launchers use")

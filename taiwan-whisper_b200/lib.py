@@ -16,7 +16,7 @@ TW_F32, TW_BF16, TW_I16, TW_I32 = 0, 1, 2, 3
 # every symbol include/twb200.h declares (tests check the library exports each one)
 EXPORTS = [
     "tw_abi_version", "tw_ctx_create", "tw_ctx_destroy", "tw_last_error", "tw_launch_count", "tw_logmel",
-    "tw_model_load", "tw_model_free", "tw_model_bytes", "tw_workspace_bytes", "tw_encode", "tw_decode_greedy", "tw_transcribe_host",
+    "tw_model_load", "tw_model_free", "tw_model_bytes", "tw_model_get_desc", "tw_workspace_bytes", "tw_encode", "tw_decode_greedy", "tw_transcribe_host",
     "tw_last_stage_ms", "tw_debug_gemm", "tw_profile", "tw_debug_set_pdl", "tw_decoder_logits", "tw_debug_attention", "tw_debug_self_attention_paged",
     "tw_debug_decode_attention", "tw_debug_encoder_attention", "tw_debug_self_attention",
 ]
@@ -69,6 +69,7 @@ def load_library() -> C.CDLL:
     lib.tw_model_free.restype = None
     lib.tw_model_bytes.argtypes = [vp]
     lib.tw_model_bytes.restype = C.c_size_t
+    lib.tw_model_get_desc.argtypes = [vp, C.POINTER(ModelDesc)]
     lib.tw_workspace_bytes.argtypes = [C.POINTER(ModelDesc)]
     lib.tw_workspace_bytes.restype = C.c_size_t
     lib.tw_encode.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, vp]

@@ -37,15 +37,26 @@ class TranscriptionInfo(NamedTuple):
     n_windows: int
 
 
-def segments_from_tokens(tokens: Sequence[int], timestamp_begin: int, eos: int, window_start_s: float, window_len_s: float):
+def segments_from_tokens(tokens: Sequence[int], timestamp_begin: int, eos: int, window_start_s: float, window_len_s: float,
+                         pad: Optional[int] = None, length: Optional[int] = None):
     """Split one decoded window at its timestamp tokens: `<|t0|> text <|t1|>` is one segment; a second timestamp right
     after a closing one opens the next segment; text without a closing timestamp runs to the end of the window.
-    Ids >= eos that are not timestamps (special tokens) never reach the text.  Returns [(start_s, end_s, [ids])]."""
+    Ids >= eos that are not timestamps (special tokens) never reach the text.  `generate()` right-pads the rows of a batch
+    with pad_token_id, which is a *text-range* id when pad != eos (50256 in large-v3's config.json): pass the row's
+    `length`, or `pad` to drop the trailing padding, so that it is neither appended as text nor opens a segment.
+    Returns [(start_s, end_s, [ids])]."""
+    tokens = [int(t) for t in tokens]
+    if length is not None:
+        tokens = tokens[:int(length)]
+    elif pad is not None:
+        n = len(tokens)
+        while n > 0 and tokens[n - 1] == pad:
+            n -= 1
+        tokens = tokens[:n]
     out = []
     start = None
     cur: List[int] = []
     for t in tokens:
-        t = int(t)
         if t >= timestamp_begin:
             ts = min((t - timestamp_begin) * TIME_PRECISION, window_len_s)
             if cur:                                   # closes the running segment
@@ -137,15 +148,16 @@ class B200BatchedInferencePipeline:
         gc = self.model.generation_config
         tsb = int(gc.no_timestamps_token_id) + 1
         eos = int(gc.eos_token_id if not isinstance(gc.eos_token_id, (list, tuple)) else gc.eos_token_id[0])
+        pad = int(gc.pad_token_id) if getattr(gc, "pad_token_id", None) is not None else eos
         segments: List[Segment] = []
         for b0 in range(0, n_win, bs):
             ids = self.model.generate(feats[b0:b0 + bs], max_length=self.max_length, num_beams=1, return_timestamps=True,
-                                      language=language or self.language, task=task, seek_loop=False)
+                                      language=language or self.language, task=task, seek_loop=False, return_prompt=False)
             ids = ids.cpu().numpy()
             for j in range(ids.shape[0]):
                 w = b0 + j
                 w_len = min(self.chunk_length, max(0.0, len(x) / SAMPLING_RATE - w * self.chunk_length))
-                for s, e, toks in segments_from_tokens(ids[j], tsb, eos, w * self.chunk_length, w_len):
+                for s, e, toks in segments_from_tokens(ids[j], tsb, eos, w * self.chunk_length, w_len, pad=pad):
                     text = self.decode_fn(toks) if self.decode_fn is not None else " ".join(str(t) for t in toks)
                     segments.append(Segment(s, e, text, toks))
             if log_progress:

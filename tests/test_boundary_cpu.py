@@ -64,6 +64,7 @@ def _fake_model(vocab=51866, multilingual=True):
     m.generation_config = gc
     m.config = types.SimpleNamespace(decoder_start_token_id=ids.sot)
     m.handle = None
+    m.output_layout = "4.45"
     return m, ids
 
 
@@ -81,6 +82,16 @@ def test_init_tokens_match_reference_prompt():
     m3, _ = _fake_model(51865, multilingual=False)
     with pytest.raises(ValueError):
         m3._init_tokens("zh", "transcribe", False)
+    # language=None on a multilingual checkpoint would need HF's language detection: refuse, never guess <|en|>
+    with pytest.raises(NotImplementedError):
+        m._init_tokens(None, "transcribe", False)
+    assert m3._init_tokens(None, None, False) == [50258, 50363 - 1 + 1]      # English-only: <|sot|><|notimestamps|>
+
+
+def test_output_layout_argument():
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration as M
+    with pytest.raises(ValueError):
+        M(hf_model=None, output_layout="4.46")
 
 
 def test_rules_struct():

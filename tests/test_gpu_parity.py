@@ -554,20 +554,37 @@ def test_torch_ops_registered():
     _cuda()
     import taiwan_whisper_b200.host  # noqa: F401
     x = torch.from_numpy(synth_batch(0, 1)).cuda()
-    out = torch.ops.twb200.log_mel(x, 80)
+    out = torch.ops.twb200.log_mel(x, None, 80)
     assert out.shape == (1, 80, 3000)
-    # model-level ops go through the handle registry: encoder -> greedy ids / teacher logits
-    from tests.gpu_common import b200_model
-    m = b200_model("tiny", "f32")
-    enc = torch.ops.twb200.encoder_forward(m._id, out)
-    assert torch.equal(enc, m.encode(out))
-    P = prompt_ids(SHAPES["tiny"].vocab, False)
-    packed = torch.ops.twb200.greedy_generate(m._id, enc, P, 16, False)
-    toks, lens = m.decode(enc, P, 16, False)
-    assert torch.equal(packed[:, :-1], toks) and torch.equal(packed[:, -1], lens)
-    ids = torch.tensor([P + [11, 12, 13]], device="cuda")
-    lg = torch.ops.twb200.decoder_logits(m._id, enc, ids)
-    assert lg.shape == (1, 7, SHAPES["tiny"].vocab) and lg.is_contiguous() and torch.equal(lg, m.decoder_logits(enc, ids))
+    nv = torch.tensor([16000], dtype=torch.int32, device="cuda")          # n_valid: only the first second is audio
+    short = torch.ops.twb200.log_mel(x, nv, 80)
+    x0 = x.clone(); x0[:, 16000:] = 0
+    assert torch.equal(short, torch.ops.twb200.log_mel(x0, None, 80))
+    # model-level ops take the raw tw_model* (what model_create returns); no Python object is involved
+    from tests.gpu_common import b200_model, hf_model
+    from taiwan_whisper_b200 import lib as twlib
+    sh = SHAPES["tiny"]
+    sd = {k: v.detach().cuda() for k, v in hf_model("tiny").state_dict().items() if k.startswith("model.")}
+    desc = [sh.d_model, sh.ffn, sh.heads, sh.enc_layers, sh.dec_layers, sh.n_mel, sh.vocab, sh.max_target, twlib.TW_F32, 2]
+    h = torch.ops.twb200.model_create(desc, "\n".join(sd.keys()), list(sd.values()))
+    assert isinstance(h, int) and h != 0
+    try:
+        m = b200_model("tiny", "f32")
+        enc = torch.ops.twb200.encoder_forward(h, out)
+        assert torch.equal(enc, m.encode(out))
+        P = prompt_ids(sh.vocab, False)
+        r = m._rules(False)
+        packed = torch.ops.twb200.greedy_generate(h, enc, P, 16, r["suppress"], r["begin_suppress"], r["eos"], r["pad"], -1,
+                                                  r["no_timestamps"], -1 if r["max_initial_ts"] is None else r["max_initial_ts"])
+        toks, lens = m.decode(enc, P, 16, False)
+        assert torch.equal(packed[:, :-1], toks) and torch.equal(packed[:, -1], lens)
+        ids = torch.tensor([P + [11, 12, 13]], device="cuda")
+        lg = torch.ops.twb200.decoder_logits(h, enc, ids)
+        assert lg.shape == (1, 7, sh.vocab) and lg.is_contiguous() and torch.equal(lg, m.decoder_logits(enc, ids))
+        # the class's own handle is the same kind of object
+        assert torch.equal(torch.ops.twb200.encoder_forward(m.handle, out), enc)
+    finally:
+        torch.ops.twb200.model_free(h)
 
 
 @pytest.mark.parametrize("chunk_length", [30, 7])

@@ -1,0 +1,355 @@
+"""-m gpu parity at the BENCHED widths and batch sizes: large-v3 width (d 1280 / 20 heads / ffn 5120 /
+V 51866 / 128 mel) at B = 64, max_length 256, and medium width (d 1024 / 16 heads / V 51865 / 80 mel) at B = 32 with the
+timestamp rules and max_length 448 (ref prefiltering/validator_inference.py:41-47) — 2 + 2 layers so that the numpy oracle
+finishes in seconds, every other dimension as benched: the M = 96 000 tcgen05 GEMMs with the TMA store / reduce-add
+epilogues, split-K skinny GEMMs at K = 5120, the 64-row page-major cache, the 148-CTA K|V stream across clip boundaries.
+
+fp32 check mode: ids bit-identical to the oracle on sampled rows of the batch (first, second, middle, last).
+bf16: scored teacher-forced on EVERY position of the sampled rows against the fp32 ids, next to HF's own bf16 forward
+(cuda, same weights, same positions): our disagreements must not exceed HF-bf16's by more than a small slack.
+"""
+import numpy as np
+import pytest
+import torch
+
+from taiwan_whisper_b200.configs import SHAPES, token_ids
+from tests.helpers import default_rules, prompt_ids, weights_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+
+
+_CACHE = {}
+
+
+def _setup(shape_name, B, max_length, timestamps, rows):
+    """batch of B distinct synthetic clips; oracle (numpy) tokens for the sampled rows"""
+    key = (shape_name, B, max_length, timestamps, tuple(rows))
+    if key in _CACHE:
+        return _CACHE[key]
+    from oracle import hf_ref, logmel_np, whisper_np
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    sh = SHAPES[shape_name]
+    hf = hf_ref.build_hf_model(sh, seed=1234)
+    W = weights_np(hf)
+    pcm = synth_batch(0, B)
+    mel_rows = logmel_np.log_mel(dequantise(pcm[list(rows)]), sh.n_mel)
+    P = prompt_ids(sh.vocab, timestamps)
+    rules = default_rules(sh.vocab, timestamps)
+    ora = []
+    for i in range(len(rows)):
+        enc = whisper_np.encoder_forward(W, mel_rows[i], sh.heads, sh.enc_layers)
+        lt = []
+        toks = whisper_np.greedy_decode(W, enc, P, rules, max_length, sh.heads, sh.dec_layers, logits_tap=lt)
+        ora.append(dict(enc=enc, tokens=toks, logits=lt))
+    _CACHE[key] = (hf, pcm, mel_rows, P, rules, ora)
+    return _CACHE[key]
+
+
+def _b200(hf, dtype, B):
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration
+    return B200WhisperForConditionalGeneration.from_hf(hf, dtype=dtype, max_batch=B, output_layout="5.x")
+
+
+CASES = [("lv3w", 64, 256, False, (0, 1, 37, 63)), ("medw", 32, 448, True, (0, 17, 31))]
+
+
+@pytest.mark.parametrize("shape_name,B,max_length,timestamps,rows", CASES)
+def test_benched_width_fp32_bit_identical(shape_name, B, max_length, timestamps, rows):
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    sh = SHAPES[shape_name]
+    hf, pcm, mel_rows, P, rules, ora = _setup(shape_name, B, max_length, timestamps, rows)
+    m = _b200(hf, torch.float32, B)
+    try:
+        mel = log_mel(torch.from_numpy(pcm).cuda(), None, sh.n_mel)
+        assert np.abs(mel[list(rows)].cpu().numpy() - mel_rows).max() < 1e-4
+        enc = m.encode(mel)
+        for i, r in enumerate(rows):
+            ref = ora[i]["enc"]
+            err = np.abs(enc[r].cpu().numpy() - ref).max() / np.abs(ref).max()
+            assert err < 1e-4, (r, err)
+        toks, lens = m.decode(enc, P, max_length, timestamps)
+        toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+        for i, r in enumerate(rows):
+            ref = ora[i]["tokens"]
+            assert lens[r] == len(ref), (r, lens[r], len(ref))
+            assert toks[r, :len(ref)].tolist() == ref, (r, int(np.argmax(toks[r, :len(ref)] != np.asarray(ref))))
+        # rows that are not sampled ran through the same launches: sanity only (valid ids, full length for random-init)
+        assert (toks >= 0).all() and (toks < sh.vocab).all()
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("shape_name,B,max_length,timestamps,rows", CASES)
+def test_benched_width_bf16_vs_hf_bf16(shape_name, B, max_length, timestamps, rows):
+    _cuda()
+    from oracle import hf_ref
+    from taiwan_whisper_b200.host import log_mel
+    sh = SHAPES[shape_name]
+    hf, pcm, mel_rows, P, rules, ora = _setup(shape_name, B, max_length, timestamps, rows)
+    n_gen = max_length - len(P)
+    n_min = min(len(o["tokens"]) for o in ora)
+    assert n_min == n_gen, "random-init rows run to the budget"
+    m = _b200(hf, torch.bfloat16, B)
+    try:
+        mel = log_mel(torch.from_numpy(pcm).cuda(), None, sh.n_mel)
+        enc = m.encode(mel)
+        for i, r in enumerate(rows):             # bf16 encoder output at the benched width: 2e-2 relative L2
+            ref = ora[i]["enc"]
+            rel = np.linalg.norm(enc[r].float().cpu().numpy() - ref) / np.linalg.norm(ref)
+            assert rel < 2e-2, (r, rel)
+        # teacher forcing: sampled rows get the oracle's fp32 ids, the others a free-running first pass of this model
+        free, _ = m.decode(enc, P, max_length, timestamps)
+        forced = free.clone()
+        for i, r in enumerate(rows):
+            forced[r] = torch.tensor(ora[i]["tokens"], dtype=torch.int32)
+        toks, _ = m.decode(enc, P, max_length, timestamps, forced=forced)
+        toks = toks.cpu().numpy()
+    finally:
+        m.close()
+    ref = np.asarray([o["tokens"] for o in ora])
+    ours_dis = int((toks[list(rows)] != ref).sum())
+    hf_ids = hf_ref.hf_teacher_forced_argmax(hf, mel_rows, P, ref, rules, device="cuda", dtype=torch.bfloat16)
+    hf_dis = int((hf_ids != ref).sum())
+    total = ref.size
+    # positions with a solid fp32 margin must agree (the 99.5 % bar of north_star); all positions: no worse than HF bf16
+    solid = solid_ok = 0
+    for i in range(len(rows)):
+        for s in range(n_gen):
+            lg = ora[i]["logits"][s]
+            top2 = np.partition(lg[np.isfinite(lg)], -2)[-2:]
+            if top2[1] - top2[0] > 0.02:
+                solid += 1
+                solid_ok += int(toks[rows[i], s] == ref[i, s])
+    print(f"{shape_name}: bf16 teacher-forced disagreements ours {ours_dis}/{total}, HF bf16 {hf_dis}/{total}; "
+          f"fp32-margin>0.02: {solid_ok}/{solid}")
+    assert solid > 0 and solid_ok / solid >= 0.995
+    assert ours_dis <= hf_dis + max(4, hf_dis // 2), (ours_dis, hf_dis, total)
+
+
+@pytest.mark.parametrize("B,dtype_name", [(70, "f32"), (130, "f32"), (130, "bf16")])
+def test_decode_batches_beyond_64(B, dtype_name):
+    """B > 64 leaves the skinny GEMM (and its fused cache append): the K|V rows must still reach the paged cache
+    (the BN=256 tile ignored the column split).  tiny, distinct clips, sampled rows vs the oracle."""
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    sh = SHAPES["tiny"]
+    rows = (0, 64, B - 1)
+    max_length = 20
+    hf, pcm, mel_rows, P, rules, ora = _setup("tiny", B, max_length, False, rows)
+    dtype = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype_name]
+    m = _b200(hf, dtype, B)
+    try:
+        mel = log_mel(torch.from_numpy(pcm).cuda(), None, sh.n_mel)
+        enc = m.encode(mel)
+        ref = np.asarray([o["tokens"] for o in ora])
+        if dtype_name == "f32":
+            toks, lens = m.decode(enc, P, max_length, False)
+            toks = toks.cpu().numpy()
+            for i, r in enumerate(rows):
+                assert toks[r].tolist() == ref[i].tolist(), r
+        else:
+            free, _ = m.decode(enc, P, max_length, False)
+            forced = free.clone()
+            for i, r in enumerate(rows):
+                forced[r] = torch.tensor(ref[i], dtype=torch.int32)
+            toks, _ = m.decode(enc, P, max_length, False, forced=forced)
+            toks = toks.cpu().numpy()
+            solid = ok = 0
+            for i, r in enumerate(rows):
+                for s in range(ref.shape[1]):
+                    lg = ora[i]["logits"][s]
+                    top2 = np.partition(lg[np.isfinite(lg)], -2)[-2:]
+                    if top2[1] - top2[0] > 0.02:
+                        solid += 1
+                        ok += int(toks[r, s] == ref[i, s])
+            assert solid > 0 and ok == solid, (ok, solid)
+    finally:
+        m.close()
+
+
+# ---------------------------------------------------------------------------------------- EOS / finished rows
+def _eos_model(shape_name, scale, seed):
+    """random-init never emits EOS (its embedding row is the zeroed padding_idx): give <|endoftext|> a random embedding of
+    `scale` x the init std so that it wins at different steps for different clips (found with the oracle)."""
+    import copy
+    from oracle import hf_ref
+    sh = SHAPES[shape_name]
+    hf = copy.deepcopy(hf_ref.build_hf_model(sh, seed=1234))
+    eos = token_ids(sh.vocab).eos
+    vec = np.random.default_rng(seed).normal(0, 0.02 * scale, sh.d_model).astype(np.float32)
+    with torch.no_grad():
+        hf.model.decoder.embed_tokens.weight[eos] = torch.from_numpy(vec)
+    return hf
+
+
+@pytest.mark.parametrize("scale,seed,expect", [(6.0, 7, "ragged"), (5.5, 9, "all_early")])
+@pytest.mark.parametrize("graph", [True, False])
+def test_eos_finished_rows_fp32(scale, seed, expect, graph, monkeypatch):
+    """EOS / finished-row path on the production step (CUDA graph replay and plain launches): rows that emit EOS at different
+    steps, pad emission afterwards, out_lengths at the EOS position, the asynchronous all-finished read-back with its
+    early exit and the pad fill of the unwritten tail — ids, lengths and padding equal to the oracle, twice (second call
+    replays the cached graph)."""
+    _cuda()
+    from oracle import logmel_np, whisper_np
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    shape_name, n, max_length = "micro128", 5, 48
+    sh = SHAPES[shape_name]
+    ids = token_ids(sh.vocab)
+    hf = _eos_model(shape_name, scale, seed)
+    W = weights_np(hf)
+    pcm = synth_batch(0, n)
+    mel = logmel_np.log_mel(dequantise(pcm), sh.n_mel)
+    P, rules = prompt_ids(sh.vocab, False), default_rules(sh.vocab, False)
+    ref = [whisper_np.greedy_decode(W, whisper_np.encoder_forward(W, mel[b], sh.heads, sh.enc_layers), P, rules, max_length,
+                                    sh.heads, sh.dec_layers) for b in range(n)]
+    n_gen = max_length - len(P)
+    lens_ref = [len(r) for r in ref]
+    if expect == "ragged":
+        assert len(set(lens_ref)) > 1 and max(lens_ref) == n_gen and min(lens_ref) < n_gen - 8, lens_ref
+    else:
+        assert max(lens_ref) < n_gen - 16, lens_ref          # every row finishes early: the early exit must fire
+    monkeypatch.setenv("TWB200_GRAPH", "1" if graph else "0")
+    m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.float32, max_batch=n, output_layout="5.x")
+    try:
+        enc = m.encode(torch.from_numpy(mel).cuda())
+        for call in range(2):
+            toks, lens = m.decode(enc, P, max_length, False)
+            toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+            assert lens.tolist() == lens_ref, (call, lens.tolist(), lens_ref)
+            for b in range(n):
+                assert toks[b, :lens_ref[b]].tolist() == ref[b], (call, b)
+                # HF: the EOS itself then pad for finished rows (generation/utils.py:2793-2805); pad == eos here
+                assert (toks[b, lens_ref[b]:] == ids.pad).all(), (call, b, toks[b].tolist())
+        out = m.generate(torch.from_numpy(mel), max_length=max_length, num_beams=1, return_timestamps=False, language="zh",
+                         task="transcribe").numpy()
+        assert out.shape == (n, max(lens_ref))
+        for b in range(n):
+            assert out[b, :lens_ref[b]].tolist() == ref[b] and (out[b, lens_ref[b]:] == ids.pad).all()
+        # the fused host-buffer entry point shares the loop
+        pt, pl = m.transcribe_pcm(torch.from_numpy(pcm), max_length)
+        assert pl.tolist() == lens_ref
+        for b in range(n):
+            assert pt[b, :lens_ref[b]].tolist() == ref[b] and (pt[b, lens_ref[b]:] == ids.pad).all()
+    finally:
+        m.close()
+
+
+def test_eos_finished_rows_bf16_structure():
+    """bf16 production path with rows finishing at different steps: structural invariants (no id after a row's length except
+    pad, lengths within budget, lengths mostly equal to the fp32 oracle's) on the graph-replayed step."""
+    _cuda()
+    from oracle import logmel_np, whisper_np
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    shape_name, n, max_length = "micro128", 5, 48
+    sh = SHAPES[shape_name]
+    ids = token_ids(sh.vocab)
+    hf = _eos_model(shape_name, 6.0, 7)
+    pcm = synth_batch(0, n)
+    mel = logmel_np.log_mel(dequantise(pcm), sh.n_mel)
+    P = prompt_ids(sh.vocab, False)
+    n_gen = max_length - len(P)
+    m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=n, output_layout="5.x")
+    try:
+        enc = m.encode(torch.from_numpy(mel).cuda())
+        for call in range(2):
+            toks, lens = m.decode(enc, P, max_length, False)
+            toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+            assert ((lens >= 0) & (lens <= n_gen)).all()
+            for b in range(n):
+                assert (toks[b, :lens[b]] != ids.eos).all()
+                assert (toks[b, lens[b]:] == ids.pad).all(), (b, toks[b].tolist())
+            assert len(set(lens.tolist())) > 1, lens.tolist()          # some rows finish, some run to the budget
+    finally:
+        m.close()
+
+
+# ---------------------------------------------------------------------------------------- call-site replay
+def test_call_site_replay_validator_and_pseudo_labelling():
+    """The exact statement sequences of the two reference call sites, run once against the HF objects and once against the
+    swapped B200 objects on the same inputs and weights:
+      ref prefiltering/validator_inference.py:55-87  fe(list, sampling_rate=16000) -> fe.pad(..., return_tensors="pt") ->
+                                                     model.generate(batch["input_features"], max_length=448, num_beams=1,
+                                                                    return_timestamps=True, language='zh', task='transcribe')
+      ref training/run_pseudo_labelling.py:864-918   gen_kwargs {max_length, num_beams, return_timestamps, language, task};
+                                                     generate_fn(batch["input_features"].to(dtype=torch_dtype), **gen_kwargs)
+    and the reference's own post-processing of the ids (filter_eot_tokens :837-843, add_concatenated_text :1003-1012) on the
+    4.45-layout output."""
+    _cuda()
+    from oracle import hf_ref
+    from taiwan_whisper_b200.host import B200WhisperFeatureExtractor, B200WhisperForConditionalGeneration
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    sh = SHAPES["tiny"]
+    tid = token_ids(sh.vocab)
+    hf = hf_ref.build_hf_model(sh, seed=1234)
+    hf_fe = hf_ref.build_hf_feature_extractor(sh.n_mel)
+    arrays = [a[: 480000 - 1234 * i] for i, a in enumerate(dequantise(synth_batch(0, 3)))]       # ragged lengths, float32
+    features = [{"idx": 10 + i, "array": a} for i, a in enumerate(arrays)]
+
+    # ---- validator_inference.py collate_fn + generate, statement for statement
+    def validator(fe, model, max_length):
+        gen_kwargs = {"max_length": max_length, "num_beams": 1, "return_timestamps": True, "language": 'zh', "task": 'transcribe'}
+        inputs = fe([feature['array'] for feature in features], sampling_rate=16000)
+        input_features = {'input_features': inputs.input_features}
+        batch = fe.pad(input_features, padding="longest", return_tensors="pt")
+        batch['idx'] = torch.from_numpy(np.array([feature['idx'] for feature in features])).long().to(batch['input_features'].device)
+        with torch.no_grad():
+            output_ids = model.generate(batch["input_features"], **gen_kwargs)
+        return batch['idx'].cpu().numpy(), output_ids
+
+    max_length = 40
+    idx_hf, ids_hf = validator(hf_fe, hf, max_length)
+    m5 = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.float32, max_batch=4, output_layout="5.x")
+    m445 = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.float32, max_batch=4)          # default: the reference's pin
+    try:
+        for fe in (B200WhisperFeatureExtractor.from_hf(hf_fe), B200WhisperFeatureExtractor(feature_size=sh.n_mel, keep_on_device=True)):
+            idx_b, ids_b = validator(fe, m5, max_length)
+            assert idx_b.tolist() == idx_hf.tolist() == [10, 11, 12]
+            assert ids_b.shape == ids_hf.shape and torch.equal(ids_b.cpu(), ids_hf.cpu()), (ids_b.tolist(), ids_hf.tolist())
+        # keep_on_device: the features never left the GPU between fe() and generate()
+        fe_dev = B200WhisperFeatureExtractor(feature_size=sh.n_mel, keep_on_device=True)
+        inputs = fe_dev([f['array'] for f in features], sampling_rate=16000)
+        assert all(t.is_cuda for t in inputs.input_features)
+        assert fe_dev.pad({'input_features': inputs.input_features}, padding="longest", return_tensors="pt")["input_features"].is_cuda
+
+        # ---- run_pseudo_labelling.py: gen_kwargs as built at :864-876, call as at :917-918
+        def pseudo_label(model, feats, torch_dtype, return_timestamps):
+            gen_kwargs = {"max_length": max_length, "num_beams": getattr(model.generation_config, "num_beams", 1),
+                          "return_timestamps": return_timestamps}
+            if hasattr(model.generation_config, "is_multilingual") and model.generation_config.is_multilingual:
+                gen_kwargs.update({"language": "zh", "task": "transcribe"})
+            model.generation_config.forced_decoder_ids = None
+            model.config.forced_decoder_ids = None
+            generate_fn = model.generate
+            return generate_fn(feats.to(dtype=torch_dtype), **gen_kwargs)
+
+        feats_pt = hf_fe.pad({"input_features": hf_fe(arrays, sampling_rate=16000).input_features}, padding="longest", return_tensors="pt")["input_features"]
+        for ts in (False, True):
+            g_hf = pseudo_label(hf, feats_pt, torch.float32, ts)
+            g_b = pseudo_label(m5, feats_pt, torch.float32, ts)
+            assert torch.equal(g_b.cpu(), g_hf.cpu()), ts
+            # the 4.45 layout the reference's code slices: forced prompt first, one pass per window
+            g_445 = pseudo_label(m445, feats_pt, torch.float32, ts).cpu().numpy()
+            prompt = [tid.sot, tid.lang_to_id["<|zh|>"], tid.transcribe] + ([] if ts else [tid.notimestamps])
+            assert (g_445[:, :len(prompt)] == np.asarray(prompt)).all()
+            single = m5.generate(feats_pt, max_length=max_length, num_beams=1, return_timestamps=ts, language="zh", task="transcribe",
+                                 seek_loop=False).cpu().numpy()
+            assert np.array_equal(g_445[:, len(prompt):], single)
+            # ref :837-843 filter_eot_tokens and :1003-1012 add_concatenated_text on that output
+            decoder_eot_token_id, decoder_prev_token_id, timestamp_position = tid.eos, tid.startofprev, 3
+            eval_preds = [row.tolist() for row in g_445]
+            for token_ids_row, gen_row in zip(eval_preds, single):
+                no_eot = [t for t in token_ids_row if t != decoder_eot_token_id]
+                prompt_ids_ = [decoder_prev_token_id] + no_eot[timestamp_position:]
+                expect = ([] if ts else [tid.notimestamps]) + [int(t) for t in gen_row if t != decoder_eot_token_id]
+                assert prompt_ids_ == [decoder_prev_token_id] + expect
+    finally:
+        m5.close()
+        m445.close()

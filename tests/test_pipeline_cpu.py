@@ -102,3 +102,87 @@ def test_segments_properties_random_streams():
         assert [t for s in segs for t in s[2]] == [t for t in toks if t < EOS]
         for s0, s1, ids in segs:
             assert ids and w0 <= s0 <= w0 + wl + 1e-9 and w0 <= s1 <= w0 + wl + 1e-9
+
+
+class _StubTokenizer:
+    """Duck-typed tokenizer for HF's module-level `_decode_asr` (needs no vocabulary files): text of a token list is the
+    comma-joined ids, so the chunks' token lists can be read back."""
+
+    def __init__(self):
+        self.all_special_ids = list(range(EOS, TSB))
+
+    def convert_tokens_to_ids(self, tok):
+        return {"<|notimestamps|>": IDS.notimestamps, "<|startofprev|>": IDS.startofprev, "<|startoftranscript|>": IDS.sot}[tok]
+
+    def _strip_prompt(self, token_ids, prompt_token_id, decoder_start_token_id):
+        if token_ids and token_ids[0] == prompt_token_id:
+            return token_ids[token_ids.index(decoder_start_token_id):] if decoder_start_token_id in token_ids else []
+        return token_ids
+
+    def decode(self, ids):
+        return "".join(f"{int(t)}," for t in ids)
+
+
+def _random_window_tokens(rng, t_lo, t_hi):
+    """a plausible timestamp-mode window: <|t0|> text <|t1|><|t1|> text <|t2|> ... with times inside [t_lo, t_hi] seconds"""
+    toks, t = [], t_lo
+    while t < t_hi - 0.5 and len(toks) < 60:
+        toks.append(ts(t))
+        toks += [int(x) for x in rng.integers(0, 300, size=int(rng.integers(1, 6)))]
+        t = min(t_hi, t + float(rng.integers(25, 400)) * 0.02)
+        if rng.random() < 0.15:
+            break                                   # window ends without a closing timestamp
+        toks.append(ts(t))
+    return toks
+
+
+def test_stitch_windows_timestamps_matches_hf_decode_asr():
+    """Timestamp-aware stitching == HF `_decode_asr(..., return_timestamps=True)` (called at ref training/flax/distil_whisper/
+    pipeline.py:353-375) on random overlapping windows: strides in seconds, timestamps inside the strides, windows that end
+    without a closing timestamp, special tokens, and the seek-loop case of several segments inside one window's ids."""
+    import numpy as np
+    import torch
+    from transformers.models.whisper.tokenization_whisper import _decode_asr
+    from taiwan_whisper_b200.longform import stitch_windows_timestamps
+    rng = np.random.default_rng(17)
+    tok = _StubTokenizer()
+    n_checked = 0
+    for case in range(150):
+        n_win = int(rng.integers(1, 6))
+        outs = []
+        for w in range(n_win):
+            sl = 0.0 if w == 0 else 5.0
+            sr = 0.0 if w == n_win - 1 else 5.0
+            chunk_len = 30.0 if w < n_win - 1 else float(rng.integers(8, 31))
+            toks = _random_window_tokens(rng, 0.0, chunk_len)
+            if rng.random() < 0.2:                  # long-form generate(): a second 30 s segment concatenated in the same ids
+                toks += _random_window_tokens(rng, 0.0, 20.0)
+            if rng.random() < 0.3:
+                toks.insert(int(rng.integers(0, len(toks) + 1)), int(rng.integers(EOS, TSB)))       # a stray special token
+            o = {"tokens": toks}
+            if case % 5 != 4:                       # every fifth case: no stride entries at all
+                o["stride"] = (chunk_len, sl, sr)
+            outs.append(o)
+        hf_in = [{**o, "tokens": torch.tensor([o["tokens"]])} for o in outs]
+        text, opt = _decode_asr(tok, hf_in, return_timestamps=True, return_language=False, time_precision=0.02)
+        mine = stitch_windows_timestamps(outs, TSB, tok.all_special_ids)
+        assert [c["timestamp"] for c in mine] == [c["timestamp"] for c in opt["chunks"]], case
+        assert [tok.decode(c["tokens"]) for c in mine] == [c["text"] for c in opt["chunks"]], case
+        n_checked += len(mine)
+    assert n_checked > 300
+    # prompt stripping: a leading <|startofprev|> ... <|startoftranscript|> prefix is dropped, as HF's _strip_prompt does
+    o = [{"tokens": [IDS.startofprev, 7, 8, IDS.sot, ts(0.0), 5, ts(1.0)]}]
+    got = stitch_windows_timestamps(o, TSB, tok.all_special_ids, prompt_token_id=IDS.startofprev, decoder_start_token_id=IDS.sot)
+    assert got == [{"timestamp": (0.0, 1.0), "tokens": [5]}]
+
+
+def test_segments_drop_right_padding():
+    """generate() right-pads a batch with pad_token_id; with pad != eos (50256 in large-v3's config.json) the padding is a
+    text-range id: it must neither be appended as text nor open a trailing segment."""
+    pad = 50256
+    row = [ts(0.0), 5, 6, ts(2.0)] + [pad] * 7
+    assert segments_from_tokens(row, TSB, EOS, 0.0, 30.0, pad=pad) == [(0.0, 2.0, [5, 6])]
+    assert segments_from_tokens(row, TSB, EOS, 0.0, 30.0, length=4) == [(0.0, 2.0, [5, 6])]
+    assert segments_from_tokens([pad] * 5, TSB, EOS, 0.0, 30.0, pad=pad) == []
+    # without the hint the old behaviour is visible (documented hazard)
+    assert segments_from_tokens(row, TSB, EOS, 0.0, 30.0)[-1][2] == [pad] * 7
