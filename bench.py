@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (fp32 check model + HF bf16 comparator)")
     ap.add_argument("--no-hf-cuda", action="store_true", help="skip the same-box HF bf16/SDPA generate comparator")
+    ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-length variant (finished rows leave the K|V stream)")
     ap.add_argument("--ref-clips", type=int, default=0, help="--impl reference: clips per step (0 = sized from K + W)")
     return ap.parse_args()
 
@@ -382,6 +383,27 @@ def main():
     ms_max = float(t.item())
     value = world * K * B * CLIP_SECONDS / (ms_max / 1000.0)
 
+    # ---------------- ragged variant: real audio ends at different lengths; rows that have finished leave the active list of
+    # the cross-attention stream.  Random-init weights never emit EOS, so the lengths come from per-row token budgets
+    # (uniform 16 .. n_gen, seeded): same kernels, same batch, device-resident inputs, K decode batches timed.
+    ragged = None
+    if rank == 0 and world == 1 and not args.no_ragged:
+        rng = np.random.default_rng(0)
+        bud = rng.integers(16, n_gen + 1, size=B)
+        model.set_row_budgets(bud.tolist())
+        step_device(0)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K):
+            step_device(W + i)
+        e1.record()
+        torch.cuda.synchronize()
+        r_ms = e0.elapsed_time(e1) / K
+        model.set_row_budgets(None)
+        ragged = {"workload": f"same batch, per-row budgets uniform 16..{n_gen} tokens (mean {bud.mean():.1f}, max {int(bud.max())}) standing in for EOS",
+                  "ms_per_step": r_ms, "value": B * CLIP_SECONDS / (r_ms / 1000.0), "unit": "audio-s/s",
+                  "generated_tokens": int(bud.sum()), "full_budget_tokens": int(B * n_gen)}
+
     # ---------------- end-to-end timing through the host API (`e2e`)
     e2e = None
     if not args.no_e2e:
@@ -458,6 +480,8 @@ def main():
                        "stage_ms_last_step": stage},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof, "stages": stages,
         }
+        if ragged is not None:
+            line["ragged"] = ragged
         if hf_cpu is not None:
             cb, ref_feats, ref_ids = cpu_baseline(args, hf_cpu)
             line["cpu_baseline"] = cb

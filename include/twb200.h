@@ -187,6 +187,11 @@ TW_API int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_co
 
 /* Test / profiling switch (calling thread): tw_debug_* launches carry the programmatic-dependent-launch attribute. */
 TW_API void tw_debug_set_pdl(int on);
+/* Test / bench hook: per-row budgets of generated tokens for the following decode calls (host array of n <= max_batch ints;
+ * n = 0 switches it off).  Row b finishes after budgets[b] tokens exactly as if it had emitted EOS next: out_lengths[b] =
+ * budgets[b], pad afterwards, the row leaves the active list of the cross-attention stream.  Random-init weights never
+ * emit EOS, so this is how the finished-row path is exercised at the benched shapes (bench.py --ragged). */
+TW_API int tw_debug_set_row_budgets(tw_model* m, const int32_t* budgets_host, int n);
 
 /* Test / profiling entry point: one GEMM of the path, C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
  * (torch nn.Linear layout), row-major dense operands.  dtype TW_BF16 (use_tc = 1: tcgen05 kernel,

@@ -268,7 +268,8 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
 template <typename T>
 __global__ void __launch_bounds__((DA_WARPS + 1) * 32, 1)
 decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
-                        const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial) {
+                        const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial,
+                        const int32_t* __restrict__ active, const int32_t* __restrict__ n_active) {
     constexpr int NW = DA_WARPS;
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
@@ -286,6 +287,10 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     // producer may start streaming it while the previous kernel (the q projection) is still running
     if (!(kv_static && warp == NW)) pdl_wait();
     if (d_tk) Tk = *d_tk + 1;
+    // active list (decode loop): only the clips that have not emitted EOS are streamed; slot s of the flat row stream is
+    // clip active[s].  The list was written by the previous step's advance kernel, which every kernel of this step is
+    // ordered after (the step's first kernel is launched with a full dependency), so it may be read before the wait.
+    if (active) B = *n_active;
     const int64_t total = (int64_t)B * Tk;
     const int R = da_rows_per_cta(total, gridDim.x);
     const int64_t row_begin = (int64_t)blockIdx.x * R;
@@ -311,9 +316,9 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
             uint32_t phase = 0;
             int64_t r = row_begin;
             while (r < row_end) {
-                const int b = (int)(r / Tk);
+                const int b = (int)(r / Tk);                         // slot in the row stream
                 const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
-                const T* src_clip = kv + (int64_t)b * kv_clip_stride;
+                const T* src_clip = kv + (int64_t)(active ? active[b] : b) * kv_clip_stride;
                 for (int64_t r0 = r; r0 < seg_end; r0 += NW) {
                     const int nrows = (int)min((int64_t)NW, seg_end - r0);
                     da_mbar_wait(da_smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -337,9 +342,9 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
     uint32_t phase = 0;
     int64_t r = row_begin;
     while (r < row_end) {
-        const int b = (int)(r / Tk);
+        const int b = (int)(r / Tk);                                 // slot in the row stream
         const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
-        const T* qb = q + (int64_t)b * q_stride;
+        const T* qb = q + (int64_t)(active ? active[b] : b) * q_stride;
         float qf[DA_MAXSLOT][8], of[DA_MAXSLOT][8], mrun[DA_MAXSLOT], lrun[DA_MAXSLOT];
 #pragma unroll
         for (int s = 0; s < DA_MAXSLOT; ++s) {
@@ -432,12 +437,18 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
 template <typename T, int HPC>
 __global__ void __launch_bounds__(HD * HPC)
 decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_t* __restrict__ d_tk, int B, int grid, int H,
-                         T* __restrict__ out) {
+                         T* __restrict__ out, const int32_t* __restrict__ active, const int32_t* __restrict__ n_active) {
     pdl_trigger();
     pdl_wait();
-    const int h = blockIdx.x * HPC + (threadIdx.x >> 6), b = blockIdx.y, e = threadIdx.x & 63;
+    const int h = blockIdx.x * HPC + (threadIdx.x >> 6), b = blockIdx.y, e = threadIdx.x & 63;      // b: slot in the row stream
     if (h >= H) return;
     if (d_tk) Tk = *d_tk + 1;
+    int clip = b;
+    if (active) {
+        B = *n_active;
+        if (b >= B) return;                  // finished clips keep their stale row (its logits are never read)
+        clip = active[b];
+    }
     const int R = da_rows_per_cta((int64_t)B * Tk, grid);
     const int c_first = (int)(((int64_t)b * Tk) / R), c_last = (int)((((int64_t)b + 1) * Tk - 1) / R);
     float m = -INFINITY;
@@ -449,7 +460,7 @@ decode_attention_combine(const float* __restrict__ partial, int Tk, const int32_
         l += rec[1] * sc;
         o += rec[2 + e] * sc;
     }
-    out[(int64_t)b * H * HD + h * HD + e] = from_f32<T>(o / l);
+    out[(int64_t)clip * H * HD + h * HD + e] = from_f32<T>(o / l);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -486,11 +497,14 @@ template <typename T, int SA_UNR>
 __global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 3 : 1)   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out, const int32_t* __restrict__ page_table,
-                             int pt_stride) {
+                             int pt_stride, const int32_t* __restrict__ finished) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
     __shared__ int32_t s_pt[SA_MAX_PAGES];
     pdl_trigger();
     const int hg = blockIdx.x, b = blockIdx.y;
+    // a clip that has emitted EOS no longer reads its cache (flags written by the previous step's select kernel; ordering
+    // as for the active list of the K|V stream kernel); the wait keeps the programmatic-dependency chain intact
+    if (finished && finished[b]) { pdl_wait(); return; }
     // the page table is fixed for the whole decode call: stage this clip's row in shared memory before the dependency wait,
     // so that the per-row page lookup is not a dependent global load in front of every K|V row fetch
     const bool pt_smem = page_table && pt_stride <= SA_MAX_PAGES;
@@ -582,15 +596,15 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
 
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                           T* out, cudaStream_t st, const int32_t* page_table, int pt_stride) {
+                           T* out, cudaStream_t st, const int32_t* page_table, int pt_stride, const int32_t* finished) {
     dim3 grid(ceil_div(H, SA_HG), B);
     launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
-                 page_table, pt_stride);
+             page_table, pt_stride, finished);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
-                                           cudaStream_t, const int32_t*, int);
+                                           cudaStream_t, const int32_t*, int, const int32_t*);
 template void self_attention_decode<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*,
-                                                   int, int, __nv_bfloat16*, cudaStream_t, const int32_t*, int);
+                                                   int, int, __nv_bfloat16*, cudaStream_t, const int32_t*, int, const int32_t*);
 
 static int g_da_sm_count = 0;
 size_t decode_attention_partial_floats(int B, int H) {
@@ -605,11 +619,12 @@ size_t decode_attention_partial_floats(int B, int H) {
 
 template <typename T>
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1, const int32_t* active,
+                      const int32_t* n_active) {
     (void)decode_attention_partial_floats(B, H);
     static const int env_stages = getenv("TWB200_DA_STAGES") ? atoi(getenv("TWB200_DA_STAGES")) : 0;      // tuning knob
     DaPlan p = da_plan(B * Tk, H, (int)sizeof(T), g_da_sm_count, env_stages >= 2 ? env_stages : DA_MAX_STAGES, DA_WARPS);
-    if (d_tk) p.G = g_da_sm_count;               // row count only known on the device: launch every CTA
+    if (d_tk || active) p.G = g_da_sm_count;     // row count only known on the device: launch every CTA
     static bool attr_set[2] = {false, false};
     const int which = sizeof(T) == 4 ? 0 : 1;
     if (!attr_set[which]) {
@@ -619,14 +634,14 @@ void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip
     if (ev0) cudaEventRecord(ev0, st);
     const int kv_static = d_tk ? 0 : 1;
     launch_k(decode_attention_stream<T>, dim3(p.G), dim3((DA_WARPS + 1) * 32), p.smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, B, H,
-             p.stages, kv_static, partial);
+             p.stages, kv_static, partial, active, n_active);
     if (ev1) cudaEventRecord(ev1, st);
     // measured (A/B, large-v3, 64 clips): 256-thread CTAs (4 heads) 1222.7 ms per decode vs 1229.8 ms with 64-thread CTAs
-    launch_k(decode_attention_combine<T, 4>, dim3(ceil_div(H, 4), B), dim3(HD * 4), 0, st, partial, Tk, d_tk, B, p.G, H, out);
+    launch_k(decode_attention_combine<T, 4>, dim3(ceil_div(H, 4), B), dim3(HD * 4), 0, st, partial, Tk, d_tk, B, p.G, H, out, active, n_active);
 }
 template void decode_attention<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*, float*,
-                                      cudaStream_t, cudaEvent_t, cudaEvent_t);
+                                      cudaStream_t, cudaEvent_t, cudaEvent_t, const int32_t*, const int32_t*);
 template void decode_attention<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*, int, int,
-                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t);
+                                              float*, __nv_bfloat16*, cudaStream_t, cudaEvent_t, cudaEvent_t, const int32_t*, const int32_t*);
 
 }  // namespace tw

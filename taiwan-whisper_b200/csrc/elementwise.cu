@@ -258,12 +258,25 @@ template void kv_append<float>(const float*, float*, const int32_t*, int, int, i
 template void kv_append<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const int32_t*, int, int, int, cudaStream_t, const int32_t*,
                                        int);
 
-__global__ void advance_step_kernel(int32_t* d_step) {
+// one warp: position += 1; active[] = ids of the clips whose finished flag is clear, in clip order (ballot + popc prefix)
+__global__ void advance_step_kernel(int32_t* d_step, DecodeState S, int B) {
     pdl_trigger();
     pdl_wait();
-    d_step[0] += 1;
+    const int lane = threadIdx.x;
+    if (lane == 0) d_step[0] += 1;
+    int n = 0;
+    for (int base = 0; base < B; base += 32) {
+        const int b = base + lane;
+        const bool live = b < B && S.finished[b] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) S.active[n + __popc(m & ((1u << lane) - 1u))] = b;
+        n += __popc(m);
+    }
+    if (lane == 0) *S.n_active = n;
 }
-void advance_step(int32_t* d_step, cudaStream_t st) { launch_k(advance_step_kernel, dim3(1), dim3(1), 0, st, d_step); }
+void advance_step(int32_t* d_step, const DecodeState& S, int B, cudaStream_t st) {
+    launch_k(advance_step_kernel, dim3(1), dim3(32), 0, st, d_step, S, B);
+}
 
 __global__ void copy_f32_kernel(const float4* __restrict__ s, float4* __restrict__ d, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];

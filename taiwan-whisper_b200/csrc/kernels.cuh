@@ -72,6 +72,7 @@ void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st);
 // h0 T [B*3000, d] -> A2 T [B*1500, 3*d], column = tap*d + channel (stride 2, pad 1)
 template <typename T>
 void im2col_conv2(const T* h0, T* out, int B, int d, cudaStream_t st);
+struct DecodeState;
 // Decode-step state lives on the device so that one captured CUDA graph can be replayed for every token:
 //   d_step[0] = pos (position of the token being fed), [1] = P (prompt length), [2] = stride of out_tokens,
 //   [3] = number of steps whose post-rules logits are tapped, [8 .. 8+P) = forced prompt tokens.
@@ -86,7 +87,8 @@ void embed_tokens_seq(const int32_t* tok, const T* E, const T* P, float* x, int 
 template <typename T>
 void kv_append(const T* qkv, T* cache, const int32_t* d_step, int B, int d, int max_len, cudaStream_t st,
                const int32_t* page_table = nullptr, int pt_stride = 0);
-void advance_step(int32_t* d_step, cudaStream_t st);
+// position += 1 and rebuild the active-clip list from the finished flags
+void advance_step(int32_t* d_step, const DecodeState& S, int B, cudaStream_t st);
 void copy_f32(const float* src, float* dst, int64_t n, cudaStream_t st);
 
 // ---- attention (attention.cu)
@@ -109,12 +111,14 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
 template <typename T>
 // d_tk (nullable): device int, the number of rows is *d_tk + 1 (self-attention cache at position pos) instead of Tk
 void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                      float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
+                      const int32_t* active = nullptr, const int32_t* n_active = nullptr);
 size_t decode_attention_partial_floats(int B, int H);
 // single-launch self-attention over the short decoder cache (Tk = *d_tk + 1 when d_tk is given)
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
-                           T* out, cudaStream_t st, const int32_t* page_table = nullptr, int pt_stride = 0);   // size of the partial workspace
+                           T* out, cudaStream_t st, const int32_t* page_table = nullptr, int pt_stride = 0,
+                           const int32_t* finished = nullptr);
 
 // ---- token selection (select.cu)
 struct RulesDev {
@@ -130,6 +134,13 @@ struct DecodeState {
     int32_t* prev_tok;    // [B] history[-2]
     int32_t* last_ts;     // [B] most recent timestamp token in the history (or -1)
     int32_t* n_unfinished;  // [1]
+    // clips that have not emitted EOS, compacted in clip order, and their count: rebuilt by advance_step at the end of every
+    // step, consumed by the cross-attention K|V stream (finished clips are not streamed) — see attention.cu
+    int32_t* active;      // [B]
+    int32_t* n_active;    // [1]
+    // optional per-row budget of generated tokens (test / bench hook, tw_debug_set_row_budgets): row b finishes after
+    // row_budget[b] tokens exactly as if it had emitted EOS there; null = off
+    const int32_t* row_budget;
 };
 // one CTA per row: rules -> argmax -> finished/pad bookkeeping -> next input token
 // (inside the forced prompt it only feeds the next prompt token)

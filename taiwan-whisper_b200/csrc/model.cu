@@ -82,10 +82,10 @@ struct LayerW {
 }  // namespace
 
 struct GraphKey {
-    int B, eos, pad, ts_begin, no_ts, max_init;
+    int B, eos, pad, ts_begin, no_ts, max_init, budget;
     bool operator<(const GraphKey& o) const {
-        return std::tie(B, eos, pad, ts_begin, no_ts, max_init) <
-               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init);
+        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, budget) <
+               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.budget);
     }
 };
 struct GraphEntry {
@@ -125,7 +125,9 @@ struct tw_model {
     float *dx = nullptr, *dlogits = nullptr, *dpartial = nullptr;
     int64_t ld_logits = 0;     // row pitch of dlogits: vocab rounded up to 4 floats (16-byte rows for the TMA-store epilogue)
     void *dxn = nullptr, *dqkv = nullptr, *datt = nullptr, *dq = nullptr, *dhmid = nullptr;
-    int32_t* dstate = nullptr;  // 6*maxB + 1 ints
+    int32_t* dstate = nullptr;  // decode state: 8 arrays of maxB ints + counters (DecodeState)
+    int32_t* d_row_budget = nullptr;   // [maxB] per-row token budgets (tw_debug_set_row_budgets)
+    bool row_budget_on = false;
     uint8_t *d_suppress = nullptr, *d_begin_suppress = nullptr;
     int32_t* d_ids_tmp = nullptr;
     int32_t *d_out_tok = nullptr, *d_out_len = nullptr;
@@ -333,7 +335,8 @@ int alloc_workspace(tw_model* m) {
     const size_t partial_floats = decode_attention_partial_floats((int)B, D.heads);
     TW_CHECK(dev_alloc(m, (void**)&m->dpartial, partial_floats * sizeof(float)));
     TW_CUDA_OK(m->ctx, cudaMemset(m->dpartial, 0, partial_floats * sizeof(float)));
-    TW_CHECK(dev_alloc(m, (void**)&m->dstate, (6 * B + 4) * sizeof(int32_t)));
+    TW_CHECK(dev_alloc(m, (void**)&m->dstate, (8 * B + 8) * sizeof(int32_t)));
+    m->d_row_budget = m->dstate + 7 * B;
     TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
     TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
     TW_CHECK(dev_alloc(m, (void**)&m->d_ids_tmp, 4096 * sizeof(int32_t)));
@@ -560,7 +563,12 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         cudaEventRecord(e, st);
         m->trace.emplace_back(e, "L" + std::to_string(l) + " " + name);
     };
+    // the step's first kernel is launched with a FULL dependency on the previous step (no programmatic early start): every
+    // later kernel of the step starts after this one did, so state written by the previous step's select / advance kernels
+    // (finished flags, active-clip list) may be read by them even ahead of their own griddepcontrol.wait
+    g_pdl = false;
     embed_tokens<T>(S.cur_tok, (const T*)m->embed, (const T*)m->dec_pos, m->d_step, x, B, d, st);
+    g_pdl = pdl_on;
     mark(-1, "embed");
     const int32_t* pt = m->d_page_table;
     for (int l = 0; l < D.dec_layers; ++l) {
@@ -584,7 +592,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
         TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
         mark(l, "qkv");
         if (!fused_append) { kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st, pt, m->kv_pages); ctx->launches += 1; }
-        self_attention_decode<T>(qkv, 3 * d, cache, 0, 0, d_pos, B, H, att, st, pt, m->kv_pages);
+        self_attention_decode<T>(qkv, 3 * d, cache, 0, 0, d_pos, B, H, att, st, pt, m->kv_pages, S.finished);
         mark(l, "self_attn");
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         mark(l, "self_o");
@@ -600,7 +608,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
             m->prof_bytes = (double)B * TW_N_CTX * 2 * d * sizeof(T);
         }
         decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial, att,
-                            st, e0, e1);
+                            st, e0, e1, S.active, S.n_active);
         mark(l, "cross_attn+combine");
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
         mark(l, "cross_o");
@@ -615,7 +623,7 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
     layernorm<T>(x, m->dec_lnf_g, m->dec_lnf_b, xn, B, d, st);
     TW_CHECK(gemm<T>(m, xn, d, (const T*)m->embed, d, B, V, d, mk_epi(EPI_F32, nullptr, m->dlogits, m->ld_logits), st));
     select_tokens(m->dlogits, m->ld_logits, V, B, m->d_step, R, S, io.out_tokens, io.out_lengths, io.forced, io.logits_tap, st);
-    advance_step(m->d_step, st);
+    advance_step(m->d_step, S, B, st);
     ctx->launches += 4;           // embed, LN, select, advance
     return TW_OK;
 }
@@ -637,7 +645,10 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     S.last_tok = m->dstate + 3 * D.max_batch;
     S.prev_tok = m->dstate + 4 * D.max_batch;
     S.last_ts = m->dstate + 5 * D.max_batch;
-    S.n_unfinished = m->dstate + 6 * D.max_batch;
+    S.active = m->dstate + 6 * D.max_batch;
+    S.row_budget = m->row_budget_on ? m->d_row_budget : nullptr;
+    S.n_unfinished = m->dstate + 8 * D.max_batch;
+    S.n_active = m->dstate + 8 * D.max_batch + 1;
     decode_state_init(S, B, prompt[0], st);
     TW_CUDA_OK(ctx, cudaMemsetAsync(out_lengths, 0, B * sizeof(int32_t), st));
     // step header -> device (pinned staging so the copy is stream-ordered)
@@ -665,7 +676,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     StepIo io{out_tokens, out_lengths, forced, logits_tap};
     if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
     if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
-    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts};
+    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, m->row_budget_on ? 1 : 0};
     cudaGraphExec_t exec = nullptr;
     uint64_t exec_kernels = 0;
 
@@ -898,7 +909,7 @@ size_t tw_workspace_bytes(const tw_model_desc* desc) {
                 al(M * d * e) + al(M * d * e) + al(M * ffn * e) + al(M * d * e) + al((size_t)D.dec_layers * M * 2 * d * e) +
                 al((size_t)D.dec_layers * B * kv_pages * TW_KV_PAGE * 2 * d * e) + al(B * kv_pages * sizeof(int32_t)) +
                 al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * ((V + 3) / 4 * 4) * f4) +
-                al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((6 * B + 4) * sizeof(int32_t)) + al(V) + al(V) +
+                al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((8 * B + 8) * sizeof(int32_t)) + al(V) + al(V) +
                 al(4096 * sizeof(int32_t)) + al(B * D.max_target * sizeof(int32_t)) + al(B * sizeof(int32_t)) + al(STEP_INTS * sizeof(int32_t));
     return w + ws;
 }
@@ -1140,6 +1151,17 @@ int tw_debug_attention(tw_ctx* ctx, const void* q, int64_t q_ld, int q_col0, con
 }
 
 void tw_debug_set_pdl(int on) { g_pdl = on != 0; }
+
+int tw_debug_set_row_budgets(tw_model* m, const int32_t* budgets_host, int n) {
+    if (!m || n < 0 || n > m->desc.max_batch || (n > 0 && !budgets_host)) return TW_E_INVALID;
+    m->row_budget_on = n > 0;
+    if (n > 0) {
+        std::vector<int32_t> tmp(m->desc.max_batch, 0x7fffffff);
+        for (int i = 0; i < n; ++i) tmp[i] = budgets_host[i] < 1 ? 1 : budgets_host[i];
+        TW_CUDA_OK(m->ctx, cudaMemcpy(m->d_row_budget, tmp.data(), tmp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    return TW_OK;
+}
 
 int tw_profile(tw_model* m, int enable, float* total_ms, int* launches, double* bytes_per_launch) {
     if (!m) return TW_E_INVALID;

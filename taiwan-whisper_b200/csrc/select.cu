@@ -75,6 +75,13 @@ select_tokens_kernel(const float* __restrict__ logits, int64_t ld_logits, int V,
         return;
     }
     if (gen_index >= out_stride) return;
+    if (S.finished[b] != 0 && !logits_tap) {     // a finished row emits pad and feeds pad; its logits are not read
+        if (threadIdx.x == 0) {
+            out_tokens[(int64_t)b * out_stride + gen_index] = R.pad;
+            S.cur_tok[b] = R.pad;
+        }
+        return;
+    }
     if (logits_tap) logits_tap = (gen_index < d_step[STEP_TAP]) ? logits_tap + (int64_t)gen_index * gridDim.x * V : nullptr;
     const float* row = logits + (int64_t)b * ld_logits;
     const bool ts_mode = R.ts_begin >= 0;
@@ -150,6 +157,8 @@ select_tokens_kernel(const float* __restrict__ logits, int64_t ld_logits, int V,
             if (was_finished) tok = R.pad;
             out_tokens[(int64_t)b * out_stride + gen_index] = tok;
             int nxt = forced ? forced[(int64_t)b * out_stride + gen_index] : tok;
+            // per-row token budget (test / bench hook): the row ends here as if this token had been followed by EOS
+            const bool budget_end = S.row_budget && gen_index + 1 >= S.row_budget[b];
             if (!was_finished) {
                 if (nxt == R.eos) {
                     S.finished[b] = 1;
@@ -161,6 +170,10 @@ select_tokens_kernel(const float* __restrict__ logits, int64_t ld_logits, int V,
                     S.last_tok[b] = nxt;
                     if (ts_mode && nxt >= R.ts_begin) S.last_ts[b] = nxt;
                     S.n_gen[b] = n_hist + 1;
+                    if (budget_end) {
+                        S.finished[b] = 1;
+                        atomicSub(S.n_unfinished, 1);
+                    }
                 }
             } else {
                 nxt = R.pad;
@@ -197,8 +210,9 @@ __global__ void decode_state_init_kernel(DecodeState S, int B, int first_tok) {
         S.last_tok[b] = -1;
         S.prev_tok[b] = -1;
         S.last_ts[b] = -1;
+        S.active[b] = b;
     }
-    if (b == 0) *S.n_unfinished = B;
+    if (b == 0) { *S.n_unfinished = B; *S.n_active = B; }
 }
 void decode_state_init(const DecodeState& st, int B, int first_tok, cudaStream_t stream) {
     decode_state_init_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(st, B, first_tok);

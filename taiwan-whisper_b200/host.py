@@ -609,6 +609,16 @@ class B200WhisperForConditionalGeneration:
         del keep
         return out_tokens, out_lengths
 
+    def set_row_budgets(self, budgets: Optional[Sequence[int]]):
+        """Test / bench hook (tw_debug_set_row_budgets): row b of the following decode calls finishes after budgets[b]
+        generated tokens exactly as if it had emitted EOS next; None switches it off.  Random-init weights never emit EOS,
+        so this is how the finished-row path (pad emission, lengths, active-clip list, early exit) runs at benched shapes."""
+        if budgets is None:
+            self.ctx.check(self.ctx.lib.tw_debug_set_row_budgets(C.c_void_p(self.handle), None, 0))
+            return
+        arr = (C.c_int32 * len(budgets))(*[int(b) for b in budgets])
+        self.ctx.check(self.ctx.lib.tw_debug_set_row_budgets(C.c_void_p(self.handle), arr, len(budgets)))
+
     def profile(self, enable: bool):
         """Reads + resets the in-situ samples of the dominant kernel, then (de)activates sampling.
         Returns (total_ms, launches); `last_profile_bytes` holds the K|V bytes of one sampled launch (one sub-batch

@@ -17,7 +17,7 @@ TW_F32, TW_BF16, TW_I16, TW_I32 = 0, 1, 2, 3
 EXPORTS = [
     "tw_abi_version", "tw_ctx_create", "tw_ctx_destroy", "tw_last_error", "tw_launch_count", "tw_logmel",
     "tw_model_load", "tw_model_free", "tw_model_bytes", "tw_model_get_desc", "tw_workspace_bytes", "tw_encode", "tw_decode_greedy", "tw_transcribe_host",
-    "tw_last_stage_ms", "tw_debug_gemm", "tw_profile", "tw_debug_set_pdl", "tw_decoder_logits", "tw_debug_attention", "tw_debug_self_attention_paged",
+    "tw_last_stage_ms", "tw_debug_gemm", "tw_profile", "tw_debug_set_pdl", "tw_debug_set_row_budgets", "tw_decoder_logits", "tw_debug_attention", "tw_debug_self_attention_paged",
     "tw_debug_decode_attention", "tw_debug_encoder_attention", "tw_debug_self_attention",
 ]
 
@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
                                        C.c_int, C.c_int, vp]
     lib.tw_debug_self_attention_paged.argtypes = [vp, vp, i64, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.tw_decoder_logits.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, i64, vp]
+    lib.tw_debug_set_row_budgets.argtypes = [vp, C.POINTER(C.c_int32), C.c_int]
     lib.tw_debug_set_pdl.argtypes = [C.c_int]
     lib.tw_debug_set_pdl.restype = None
     lib.tw_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)]

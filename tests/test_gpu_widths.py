@@ -271,6 +271,51 @@ def test_eos_finished_rows_bf16_structure():
         m.close()
 
 
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_row_budgets_prefix_property_benched_width(dtype_name):
+    """Finished-row path at the benched width and batch (large-v3 width, B = 64, max_length 256): rows are given ragged token
+    budgets (tw_debug_set_row_budgets: the row ends as if EOS followed); every row must reproduce the first budget[b] ids
+    of the unconstrained run — finished clips leave the K|V stream's active list without disturbing the others — then pad;
+    lengths == budgets; a second batch where every row stops early takes the early exit."""
+    _cuda()
+    from taiwan_whisper_b200.host import log_mel
+    shape_name, B, max_length = "lv3w", 64, 256
+    sh = SHAPES[shape_name]
+    ids = token_ids(sh.vocab)
+    hf, pcm, mel_rows, P, rules, ora = _setup(shape_name, B, max_length, False, (0, 1, 37, 63))
+    n_gen = max_length - len(P)
+    rng = np.random.default_rng(3)
+    budgets = rng.integers(1, n_gen + 1, size=B)
+    budgets[0], budgets[1], budgets[63] = n_gen, 1, 17
+    m = _b200(hf, {"f32": torch.float32, "bf16": torch.bfloat16}[dtype_name], B)
+    try:
+        mel = log_mel(torch.from_numpy(pcm).cuda(), None, sh.n_mel)
+        enc = m.encode(mel)
+        full, full_len = m.decode(enc, P, max_length, False)
+        full = full.cpu().numpy()
+        assert (full_len.cpu().numpy() == n_gen).all()
+        for bud in (budgets, np.minimum(budgets, 40)):
+            m.set_row_budgets(bud.tolist())
+            for call in range(2):
+                toks, lens = m.decode(enc, P, max_length, False)
+                toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
+                assert lens.tolist() == bud.tolist()
+                bad = 0
+                for b in range(B):
+                    assert (toks[b, bud[b]:] == ids.pad).all(), b
+                    bad += int((toks[b, :bud[b]] != full[b, :bud[b]]).sum())
+                if dtype_name == "f32":
+                    assert bad == 0
+                else:           # bf16: split-K atomics make near-ties order-dependent; free-running rows may then diverge
+                    assert bad <= 0.02 * bud.sum(), (bad, int(bud.sum()))
+            m.set_row_budgets(None)
+        again, _ = m.decode(enc, P, max_length, False)
+        if dtype_name == "f32":
+            assert np.array_equal(again.cpu().numpy(), full)
+    finally:
+        m.close()
+
+
 # ---------------------------------------------------------------------------------------- call-site replay
 def test_call_site_replay_validator_and_pseudo_labelling():
     """The exact statement sequences of the two reference call sites, run once against the HF objects and once against the
