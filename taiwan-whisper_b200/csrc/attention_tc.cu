@@ -82,6 +82,20 @@ __device__ __forceinline__ float fa_ex2(float x) {           // single MUFU.EX2 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// one elected lane of a converged warp (see tc_ptx.cuh: the single-thread roles run warp-uniform and issue under this predicate)
+__device__ __forceinline__ uint32_t fa_elect() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+    return pred;
+}
+// p = (col < valid) ? p : 0 as an opaque (volatile) select: it keeps the masked key-tile code path from being merged with
+// the unmasked one — the compiler otherwise if-converts both into ONE path that runs a compare + select per score on every
+// tile (25 M ISETP + 25 M FSEL per launch in profiles/r02_encoder_attention_ncu.md), although only the last key tile of
+// a clip (or the causal diagonal) is masked
+__device__ __forceinline__ float fa_mask0(float p, int col, int valid) {
+    asm volatile("{\n.reg .pred q;\nsetp.lt.s32 q, %1, %2;\nselp.f32 %0, %0, 0f00000000, q;\n}\n" : "+f"(p) : "r"(col), "r"(valid));
+    return p;
+}
 __device__ __forceinline__ void fa_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fa_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -119,7 +133,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     uint64_t* o_full = bars + 11;     // 1  PV done
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int d = H * FA_D;
     const int q0 = qb * FA_BQ;
@@ -157,73 +171,71 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     const uint32_t tmem_O = tmem_base + 128;      // columns [128,192)
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        if (fa_elect()) {
             fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
             fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
+            if (fa_elect()) {
                 fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
                 fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), k_col0 + h * FA_D,
                                kv_base + j * FA_BK);
-                fa_mbar_wait(fa_smem_u32(&v_empty[0]), (j & 1) ^ 1);
+            }
+            __syncwarp();
+            fa_mbar_wait(fa_smem_u32(&v_empty[0]), (j & 1) ^ 1);
+            if (fa_elect()) {
                 fa_mbar_expect_tx(fa_smem_u32(&v_full[0]), FA_TILE_BYTES);
                 fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[0]), fa_smem_u32(sV), v_col0 + h * FA_D, kv_base + j * FA_BK);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
-            constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
-            const uint64_t q_desc = fa_desc(fa_smem_u32(sQ));
-            fa_mbar_wait(fa_smem_u32(q_full), 0);
-            for (int j = 0; j < n_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                // S(j) = Q K(j)^T   (S columns are free: the softmax warps arrived on p_full(j-1))
-                fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
-                if (j > 0) fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
-                fa_fence_after();
-                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                fa_commit(fa_smem_u32(&k_empty[st]));
-                fa_commit(fa_smem_u32(s_full));
-                if (j > 0) {
-                    // O_tile(j-1) = P(j-1) V(j-1): P is in shared memory since p_full(j-1)
-                    fa_mbar_wait(fa_smem_u32(&v_full[0]), (j - 1) & 1);
-                    fa_fence_after();
-                    const uint32_t v_addr = fa_smem_u32(sV);
-#pragma unroll
-                    for (int k = 0; k < FA_BK / 16; ++k) {
-                        // A: P atom (k/4), 32-byte steps inside the 128-byte swizzle row; B: 16 key rows = 2048 bytes
-                        const uint64_t p_desc = fa_desc(fa_smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2 * (k & 3);
-                        const uint64_t v_desc = fa_desc(v_addr + k * 2048);
-                        fa_mma(tmem_O, p_desc, v_desc, idesc_pv, k > 0 ? 1u : 0u);
-                    }
-                    fa_commit(fa_smem_u32(&v_empty[0]));
-                    fa_commit(fa_smem_u32(o_full));
-                }
-            }
-            {   // last P V
-                const int j = n_tiles;
-                fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
-                fa_mbar_wait(fa_smem_u32(&v_full[0]), (j - 1) & 1);
-                fa_fence_after();
-                const uint32_t v_addr = fa_smem_u32(sV);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
+        constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
+        const uint32_t q_addr = fa_smem_u32(sQ), v_addr = fa_smem_u32(sV), p_addr = fa_smem_u32(sP);
+        auto issue_pv = [&](int j) {          // O_tile(j) = P(j) V(j): P is in shared memory since p_full(j)
+            fa_mbar_wait(fa_smem_u32(p_full), j & 1);
+            fa_mbar_wait(fa_smem_u32(&v_full[0]), j & 1);
+            fa_fence_after();
+            if (fa_elect()) {
 #pragma unroll
                 for (int k = 0; k < FA_BK / 16; ++k) {
-                    const uint64_t p_desc = fa_desc(fa_smem_u32(sP + (k >> 2) * FA_TILE_BYTES)) + 2 * (k & 3);
+                    // A: P atom (k/4), 32-byte steps inside the 128-byte swizzle row; B: 16 key rows = 2048 bytes
+                    const uint64_t p_desc = fa_desc(p_addr + (k >> 2) * FA_TILE_BYTES) + 2 * (k & 3);
                     const uint64_t v_desc = fa_desc(v_addr + k * 2048);
                     fa_mma(tmem_O, p_desc, v_desc, idesc_pv, k > 0 ? 1u : 0u);
                 }
                 fa_commit(fa_smem_u32(&v_empty[0]));
                 fa_commit(fa_smem_u32(o_full));
             }
+            __syncwarp();
+        };
+        fa_mbar_wait(fa_smem_u32(q_full), 0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            // S(j) = Q K(j)^T   (S columns are free: the softmax warps arrived on p_full(j-1))
+            fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
+            if (j > 0) fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
+            fa_fence_after();
+            if (fa_elect()) {
+                const uint64_t q_desc = fa_desc(q_addr);
+                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+                fa_commit(fa_smem_u32(&k_empty[st]));
+                fa_commit(fa_smem_u32(s_full));
+            }
+            __syncwarp();
+            if (j > 0) issue_pv(j - 1);
         }
+        issue_pv(n_tiles - 1);
     } else {
         // ===================== softmax warps 0..3: thread = query row =====================
         const int r = warp * 32 + lane;                 // row inside the tile == TMEM lane
@@ -283,10 +295,9 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const bool ok0 = c + i < valid, ok1 = c + i + 1 < valid;
                         const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        const float p0 = ok0 ? fa_ex2(fmaf(s0, LOG2E, mneg)) : 0.0f;
-                        const float p1 = ok1 ? fa_ex2(fmaf(s1, LOG2E, mneg)) : 0.0f;
+                        const float p0 = fa_mask0(fa_ex2(fmaf(s0, LOG2E, mneg)), c + i, valid);
+                        const float p1 = fa_mask0(fa_ex2(fmaf(s1, LOG2E, mneg)), c + i + 1, valid);
                         lsum0 += p0;
                         lsum1 += p1;
                         __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
@@ -389,18 +400,606 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     }
 }
 
+// =====================================================================================================================
+// v2 ("instruction diet", default): same roles and tile shapes, but the softmax warps execute ~3 instructions per score
+// instead of ~6 — the round-1 profile (profiles/r01_encoder_attention_ncu.md) showed the kernel bound by the issue slots
+// and dependency stalls of the one softmax warp per SM sub-partition, not by MUFU, tensor or memory throughput:
+//   * P (bf16) is written back to TENSOR MEMORY over the score columns it was computed from (tcgen05.st, 64 columns) and
+//     P V runs with the A operand in TMEM: no shared-memory P tile, no swizzled 16-byte stores, no proxy fence;
+//   * O accumulates in TMEM across key tiles (P V with accumulate) instead of being folded into registers every tile; the
+//     exponentials use a per-row REFERENCE max that is only moved when the tile max exceeds it by more than 2^8
+//     (then O and the row sum are rescaled in TMEM, warp-uniformly skipped otherwise) — exact, because numerator and
+//     denominator carry the same reference;
+//   * the row sum is produced by the tensor core: a second MMA of P against a tile of ones accumulates sum_k P[r,k] into a
+//     TMEM column, from the same bf16-rounded P the numerator uses (no FADD per score);
+//   * the row max uses the 3-input FMNMX.
+// MMA issue order per key tile is P V (j-1) then Q K^T (j): the tensor pipe executes in order, so Q K^T (j) overwrites the
+// score / P columns only after P V (j-1) has read them, and s_full(j) implies that P V (j-1) has completed.
+constexpr int FA2_SMEM = 1024 + FA_TILE_BYTES * (1 + 2 + 2 + 1) + 256;    // Q, K x2, V x2, ones: 2 CTAs / SM
+constexpr float FA2_RESCALE_LOG2 = 8.0f;
+
+__device__ __forceinline__ void fa_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_ld1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_st1(uint32_t taddr, uint32_t r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void fa_tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fa_max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+encoder_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                             __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
+    extern __shared__ unsigned char fa_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;
+    unsigned char* sK = smem + FA_TILE_BYTES;           // 2 stages
+    unsigned char* sV = smem + 3 * FA_TILE_BYTES;       // 2 stages
+    unsigned char* sOne = smem + 5 * FA_TILE_BYTES;     // 128 x 64 bf16 ones (B operand of the row-sum MMA; any layout reads as ones)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE_BYTES);
+    uint64_t* q_full = bars;          // 1
+    uint64_t* k_full = bars + 1;      // 2
+    uint64_t* k_empty = bars + 3;     // 2
+    uint64_t* v_full = bars + 5;      // 2
+    uint64_t* v_empty = bars + 7;     // 2
+    uint64_t* s_full = bars + 9;      // 1  QK^T done (and with it every earlier MMA of this CTA)
+    uint64_t* p_full = bars + 10;     // 1  P written to TMEM (S consumed)
+    uint64_t* o_full = bars + 11;     // 1  last PV done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int d = H * FA_D;
+    const int q0 = qb * FA_BQ;
+    const int n_tiles = causal ? min((Sk + FA_BK - 1) / FA_BK, qb + 1) : (Sk + FA_BK - 1) / FA_BK;
+    const int row_base = b * S;
+    const int kv_base = b * Sk;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+        fa_mbar_init(fa_smem_u32(q_full), 1);
+        for (int i = 0; i < 2; ++i) {
+            fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&k_empty[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_empty[i]), 1);
+        }
+        fa_mbar_init(fa_smem_u32(s_full), 1);
+        fa_mbar_init(fa_smem_u32(p_full), 4);          // one arrive per softmax warp
+        fa_mbar_init(fa_smem_u32(o_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fa_smem_u32(tmem_ptr)), "r"(FA_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp < 4) {       // ones tile (bf16 1.0 = 0x3F80), generic-proxy writes made visible to the tensor core below
+        uint4* p1 = reinterpret_cast<uint4*>(sOne);
+        for (int i = threadIdx.x; i < FA_TILE_BYTES / 16; i += 128) p1[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fa_fence_before();
+    __syncthreads();
+    fa_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_S = tmem_base;            // columns [0,128): fp32 scores; P (bf16 pairs) is written over columns [0,64)
+    const uint32_t tmem_O = tmem_base + 128;      // columns [128,192): O accumulator
+    const uint32_t tmem_L = tmem_base + 192;      // columns [192,208): row sums (every column holds the same sum; column 0 is read)
+
+    if (warp == 4) {
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        if (fa_elect()) {
+            fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
+            fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
+            if (fa_elect()) {
+                fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), k_col0 + h * FA_D,
+                               kv_base + j * FA_BK);
+            }
+            __syncwarp();
+            fa_mbar_wait(fa_smem_u32(&v_empty[st]), ph ^ 1);
+            if (fa_elect()) {
+                fa_mbar_expect_tx(fa_smem_u32(&v_full[st]), FA_TILE_BYTES);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[st]), fa_smem_u32(sV + st * FA_TILE_BYTES), v_col0 + h * FA_D,
+                               kv_base + j * FA_BK);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
+        constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
+        constexpr uint32_t idesc_l = fa_idesc(128, 16, 1);
+        const uint32_t q_addr = fa_smem_u32(sQ);
+        const uint32_t one_addr = fa_smem_u32(sOne);
+        auto issue_pv = [&](int j, bool last) {          // O += P(j) V(j); L += P(j) 1     (P in TMEM: 8 columns per 16 keys)
+            const int st = j & 1;
+            fa_mbar_wait(fa_smem_u32(p_full), j & 1);
+            fa_mbar_wait(fa_smem_u32(&v_full[st]), (j >> 1) & 1);
+            fa_fence_after();
+            const uint32_t v_addr = fa_smem_u32(sV + st * FA_TILE_BYTES);
+            if (fa_elect()) {
+#pragma unroll
+                for (int k = 0; k < FA_BK / 16; ++k) {
+                    fa_mma_ts(tmem_O, tmem_S + 8 * k, fa_desc(v_addr + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    fa_mma_ts(tmem_L, tmem_S + 8 * k, fa_desc(one_addr + k * 2048), idesc_l, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                fa_commit(fa_smem_u32(&v_empty[st]));
+                if (last) fa_commit(fa_smem_u32(o_full));
+            }
+            __syncwarp();
+        };
+        fa_mbar_wait(fa_smem_u32(q_full), 0);
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j & 1;
+            const uint32_t ph = (j >> 1) & 1;
+            if (j > 0) issue_pv(j - 1, false);     // reads P(j-1) before Q K^T (j) overwrites the columns (in-order pipe)
+            fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
+            fa_fence_after();
+            if (fa_elect()) {
+                const uint64_t q_desc = fa_desc(q_addr);
+                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+                fa_commit(fa_smem_u32(&k_empty[st]));
+                fa_commit(fa_smem_u32(s_full));
+            }
+            __syncwarp();
+        }
+        issue_pv(n_tiles - 1, true);
+    } else {
+        // ===================== softmax warps 0..3: thread = query row =====================
+        const int r = warp * 32 + lane;                 // row inside the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const float LOG2E = 1.4426950408889634f;
+        float m_ref = -INFINITY;                        // reference max of this row (raw score units)
+        for (int j = 0; j < n_tiles; ++j) {
+            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
+            fa_fence_after();
+            const int valid = causal ? min(Sk - j * FA_BK, q0 + r - j * FA_BK + 1) : Sk - j * FA_BK;
+            const bool full_tile = (Sk - j * FA_BK >= FA_BK) && !(causal && j == qb);
+            // ---- pass A: row max of the tile (3-input max), the second half of the columns in flight during the first
+            float mx = -INFINITY;
+            {
+                uint32_t va[32], vb[32];
+                auto fold = [&](const uint32_t* v, int c) {
+                    if (full_tile) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+                    }
+                };
+                fa_tmem_ld32(tmem_S + lane_off, va);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); fold(va, 0);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); fold(vb, 32);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); fold(va, 64);
+                fa_tmem_wait_ld(); fold(vb, 96);
+            }
+            // ---- reference max: moved only when the tile max exceeds it by more than 2^8 (then O and L are rescaled in TMEM;
+            // P V (j-1) has completed: s_full(j) was committed after it).  Rows without a valid key (cannot happen on the
+            // paths that use this kernel) keep their reference.
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool grow = (mx - m_ref) * LOG2E > FA2_RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float f = grow ? fa_ex2((m_ref - mx) * LOG2E) : 1.0f;
+                    if (grow) m_ref = mx;
+#pragma unroll
+                    for (int c = 0; c < FA_D; c += 32) {
+                        uint32_t v[32];
+                        fa_tmem_ld32(tmem_O + lane_off + c, v);
+                        fa_tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+                        fa_tmem_st32(tmem_O + lane_off + c, v);
+                    }
+                    uint32_t lv;
+                    fa_tmem_ld1(tmem_L + lane_off, lv);
+                    fa_tmem_wait_ld();
+                    fa_tmem_st1(tmem_L + lane_off, __float_as_uint(__uint_as_float(lv) * f));
+                    fa_tmem_wait_st();
+                }
+            }
+            // ---- pass B: P = exp2((s - m_ref) log2e) -> bf16 pairs -> TMEM columns [c/2, c/2 + 16) of the score region
+            const float mneg = -m_ref * LOG2E;
+            {
+                uint32_t va[32], vb[32];
+                auto chunk = [&](const uint32_t* v, int c) {
+                    uint32_t pk[16];
+                    if (full_tile) {                       // warp-uniform: only the last key tile / the causal diagonal is masked
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg));
+                            const float p1 = fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg));
+                            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = fa_mask0(fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg)), c + i, valid);
+                            const float p1 = fa_mask0(fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)), c + i + 1, valid);
+                            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
+                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                        }
+                    }
+                    fa_tmem_st16(tmem_S + lane_off + (c >> 1), pk);
+                };
+                fa_tmem_ld32(tmem_S + lane_off, va);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); chunk(va, 0);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); chunk(vb, 32);
+                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); chunk(va, 64);
+                fa_tmem_wait_ld(); chunk(vb, 96);
+            }
+            fa_tmem_wait_st();
+            fa_fence_before();
+            __syncwarp();
+            if (lane == 0) fa_mbar_arrive(fa_smem_u32(p_full));
+        }
+        // ---- epilogue: O / L
+        fa_mbar_wait(fa_smem_u32(o_full), 0);
+        fa_fence_after();
+        uint32_t lv;
+        fa_tmem_ld1(tmem_L + lane_off, lv);
+        fa_tmem_wait_ld();
+        const float inv = 1.0f / __uint_as_float(lv);
+        const int q = q0 + r;
+        __nv_bfloat16* orow = out + ((int64_t)(row_base + q)) * d + h * FA_D;
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t v[32];
+            fa_tmem_ld32(tmem_O + lane_off + c, v);
+            fa_tmem_wait_ld();
+            if (q < S) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(orow + c + i) = pk;
+                }
+            }
+        }
+        fa_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        fa_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
+    }
+}
+
+// =====================================================================================================================
+// v3 (default): v2 with 64-key tiles and the score columns DOUBLE-BUFFERED in tensor memory, so that Q K^T of tile j+1
+// is already done when the softmax of tile j finishes: the softmax warps never wait for the tensor core in steady state
+// (in v2 they spent ~44 % of their time waiting for s_full, profiles/r02_encoder_attention_ncu.md).  With the warp-uniform
+// MMA issue a 64-key tile costs 12 back-to-back tcgen05.mma instead of 12 divergence loops, which is what made the smaller
+// tile a loss in round 1.  TMEM: S0 [0,64) | S1 [64,128) | O [128,192) | L [192,208) = 208 columns, 2 CTAs / SM.
+//   MMA issue order:  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...     (P(j) overwrites the first 32 columns of S(j&1); QK(j+2)
+//   is issued after PV(j), and the tensor pipe executes in order).  O / L are rescaled (rarely) only after pv_done(j-1).
+constexpr int FA3_BK = 64;
+constexpr int FA3_KV_BYTES = FA3_BK * FA_D * 2;       // 8 KB
+constexpr int FA3_STAGES = 4;
+constexpr int FA3_SMEM = 1024 + FA_TILE_BYTES + FA3_KV_BYTES * (2 * FA3_STAGES + 1) + 512;    // Q, K x4, V x4, ones
+
+__global__ void __launch_bounds__(FA_THREADS, 2)
+encoder_attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                             __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
+    extern __shared__ unsigned char fa_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;
+    unsigned char* sK = smem + FA_TILE_BYTES;
+    unsigned char* sV = sK + FA3_STAGES * FA3_KV_BYTES;
+    unsigned char* sOne = sV + FA3_STAGES * FA3_KV_BYTES;       // 64 x 64 bf16 ones
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOne + FA3_KV_BYTES);
+    uint64_t* q_full = bars;                       // 1
+    uint64_t* k_full = bars + 1;                   // FA3_STAGES
+    uint64_t* k_empty = k_full + FA3_STAGES;
+    uint64_t* v_full = k_empty + FA3_STAGES;
+    uint64_t* v_empty = v_full + FA3_STAGES;
+    uint64_t* s_full = v_empty + FA3_STAGES;       // 2  QK^T into score buffer b done
+    uint64_t* p_full = s_full + 2;                 // 2  P written over score buffer b
+    uint64_t* pv_done = p_full + 2;                // 1  one phase per key tile: P V (j) has completed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int d = H * FA_D;
+    const int q0 = qb * FA_BQ;
+    const int tiles_all = (Sk + FA3_BK - 1) / FA3_BK;
+    const int n_tiles = causal ? min(tiles_all, 2 * qb + 2) : tiles_all;      // causal: tiles up to the block's last query
+    const int row_base = b * S;
+    const int kv_base = b * Sk;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+        fa_mbar_init(fa_smem_u32(q_full), 1);
+        for (int i = 0; i < FA3_STAGES; ++i) {
+            fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&k_empty[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&v_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            fa_mbar_init(fa_smem_u32(&s_full[i]), 1);
+            fa_mbar_init(fa_smem_u32(&p_full[i]), 4);      // one arrive per softmax warp
+        }
+        fa_mbar_init(fa_smem_u32(pv_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fa_smem_u32(tmem_ptr)), "r"(FA_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp < 4) {       // ones tile (bf16 1.0 = 0x3F80)
+        uint4* p1 = reinterpret_cast<uint4*>(sOne);
+        for (int i = threadIdx.x; i < FA3_KV_BYTES / 16; i += 128) p1[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    fa_fence_before();
+    __syncthreads();
+    fa_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_S = tmem_base;            // two score buffers of 64 columns; P (bf16 pairs) over the first 32 of each
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_L = tmem_base + 192;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (fa_elect()) {
+            fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
+            fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_tiles; ++j) {
+            const int st = j % FA3_STAGES;
+            const uint32_t ph = (j / FA3_STAGES) & 1;
+            fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
+            if (fa_elect()) {
+                fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA3_KV_BYTES);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA3_KV_BYTES), k_col0 + h * FA_D,
+                               kv_base + j * FA3_BK);
+            }
+            __syncwarp();
+            fa_mbar_wait(fa_smem_u32(&v_empty[st]), ph ^ 1);
+            if (fa_elect()) {
+                fa_mbar_expect_tx(fa_smem_u32(&v_full[st]), FA3_KV_BYTES);
+                fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[st]), fa_smem_u32(sV + st * FA3_KV_BYTES), v_col0 + h * FA_D,
+                               kv_base + j * FA3_BK);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_qk = fa_idesc(128, FA3_BK, 0);
+        constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
+        constexpr uint32_t idesc_l = fa_idesc(128, 16, 1);
+        const uint32_t q_addr = fa_smem_u32(sQ);
+        const uint32_t one_addr = fa_smem_u32(sOne);
+        auto issue_qk = [&](int j) {
+            const int st = j % FA3_STAGES;
+            fa_mbar_wait(fa_smem_u32(&k_full[st]), (j / FA3_STAGES) & 1);
+            fa_fence_after();
+            if (fa_elect()) {
+                const uint64_t q_desc = fa_desc(q_addr);
+                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA3_KV_BYTES));
+#pragma unroll
+                for (int k = 0; k < FA_D / 16; ++k)
+                    fa_mma(tmem_S + (j & 1) * FA3_BK, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
+                fa_commit(fa_smem_u32(&k_empty[st]));
+                fa_commit(fa_smem_u32(&s_full[j & 1]));
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int j) {
+            const int st = j % FA3_STAGES;
+            fa_mbar_wait(fa_smem_u32(&p_full[j & 1]), (j >> 1) & 1);
+            fa_mbar_wait(fa_smem_u32(&v_full[st]), (j / FA3_STAGES) & 1);
+            fa_fence_after();
+            const uint32_t v_addr = fa_smem_u32(sV + st * FA3_KV_BYTES);
+            const uint32_t p_tmem = tmem_S + (j & 1) * FA3_BK;
+            if (fa_elect()) {
+#pragma unroll
+                for (int k = 0; k < FA3_BK / 16; ++k) {
+                    fa_mma_ts(tmem_O, p_tmem + 8 * k, fa_desc(v_addr + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                    fa_mma_ts(tmem_L, p_tmem + 8 * k, fa_desc(one_addr + k * 2048), idesc_l, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                fa_commit(fa_smem_u32(&v_empty[st]));
+                fa_commit(fa_smem_u32(pv_done));
+            }
+            __syncwarp();
+        };
+        fa_mbar_wait(fa_smem_u32(q_full), 0);
+        issue_qk(0);
+        if (n_tiles > 1) issue_qk(1);
+        for (int j = 0; j < n_tiles; ++j) {
+            issue_pv(j);
+            if (j + 2 < n_tiles) issue_qk(j + 2);
+        }
+    } else {
+        // ===================== softmax warps 0..3: thread = query row =====================
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const float LOG2E = 1.4426950408889634f;
+        float m_ref = -INFINITY;
+        for (int j = 0; j < n_tiles; ++j) {
+            const uint32_t sbuf = tmem_S + lane_off + (j & 1) * FA3_BK;
+            fa_mbar_wait(fa_smem_u32(&s_full[j & 1]), (j >> 1) & 1);
+            fa_fence_after();
+            const int valid = causal ? min(Sk - j * FA3_BK, q0 + r - j * FA3_BK + 1) : Sk - j * FA3_BK;
+            const bool full_tile = (Sk - j * FA3_BK >= FA3_BK) && !(causal && j >= 2 * qb);
+            // the 64 scores of this row stay in registers for both passes
+            uint32_t va[32], vb[32];
+            fa_tmem_ld32(sbuf, va);
+            fa_tmem_ld32(sbuf + 32, vb);
+            fa_tmem_wait_ld();
+            float mx = -INFINITY;
+            if (full_tile) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < valid) ? __uint_as_float(va[i]) : -INFINITY);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (32 + i < valid) ? __uint_as_float(vb[i]) : -INFINITY);
+            }
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool grow = (mx - m_ref) * LOG2E > FA2_RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, grow)) {
+                    // O and L are being accumulated by P V (j-1): wait for it, then rescale this row in tensor memory
+                    fa_mbar_wait(fa_smem_u32(pv_done), (j - 1) & 1);
+                    fa_fence_after();
+                    const float f = grow ? fa_ex2((m_ref - mx) * LOG2E) : 1.0f;
+                    if (grow) m_ref = mx;
+#pragma unroll
+                    for (int c = 0; c < FA_D; c += 32) {
+                        uint32_t v[32];
+                        fa_tmem_ld32(tmem_O + lane_off + c, v);
+                        fa_tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+                        fa_tmem_st32(tmem_O + lane_off + c, v);
+                    }
+                    uint32_t lv;
+                    fa_tmem_ld1(tmem_L + lane_off, lv);
+                    fa_tmem_wait_ld();
+                    fa_tmem_st1(tmem_L + lane_off, __float_as_uint(__uint_as_float(lv) * f));
+                    fa_tmem_wait_st();
+                }
+            }
+            const float mneg = -m_ref * LOG2E;
+            uint32_t pk[32];
+            if (full_tile) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_ex2(fmaf(__uint_as_float(va[i]), LOG2E, mneg)),
+                                                              fa_ex2(fmaf(__uint_as_float(va[i + 1]), LOG2E, mneg)));
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_ex2(fmaf(__uint_as_float(vb[i]), LOG2E, mneg)),
+                                                              fa_ex2(fmaf(__uint_as_float(vb[i + 1]), LOG2E, mneg)));
+                    pk[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_mask0(fa_ex2(fmaf(__uint_as_float(va[i]), LOG2E, mneg)), i, valid),
+                                                              fa_mask0(fa_ex2(fmaf(__uint_as_float(va[i + 1]), LOG2E, mneg)), i + 1, valid));
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_mask0(fa_ex2(fmaf(__uint_as_float(vb[i]), LOG2E, mneg)), 32 + i, valid),
+                                                              fa_mask0(fa_ex2(fmaf(__uint_as_float(vb[i + 1]), LOG2E, mneg)), 33 + i, valid));
+                    pk[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+            }
+            fa_tmem_st32(sbuf, pk);              // P(j): 64 keys = 32 columns over the scores they came from
+            fa_tmem_wait_st();
+            fa_fence_before();
+            __syncwarp();
+            if (lane == 0) fa_mbar_arrive(fa_smem_u32(&p_full[j & 1]));
+        }
+        // ---- epilogue: O / L
+        fa_mbar_wait(fa_smem_u32(pv_done), (n_tiles - 1) & 1);
+        fa_fence_after();
+        uint32_t lv;
+        fa_tmem_ld1(tmem_L + lane_off, lv);
+        fa_tmem_wait_ld();
+        const float inv = 1.0f / __uint_as_float(lv);
+        const int q = q0 + r;
+        __nv_bfloat16* orow = out + ((int64_t)(row_base + q)) * d + h * FA_D;
+#pragma unroll
+        for (int c = 0; c < FA_D; c += 32) {
+            uint32_t v[32];
+            fa_tmem_ld32(tmem_O + lane_off + c, v);
+            fa_tmem_wait_ld();
+            if (q < S) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk4;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+                    pk4.x = *reinterpret_cast<uint32_t*>(&h0); pk4.y = *reinterpret_cast<uint32_t*>(&h1);
+                    pk4.z = *reinterpret_cast<uint32_t*>(&h2); pk4.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(orow + c + i) = pk4;
+                }
+            }
+        }
+        fa_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        fa_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host ----------------------------------------------------------------------------------
 typedef CUresult (*FaEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static FaEncodeTiledFn g_fa_encode = nullptr;
 
-static int fa_map(tw_ctx* ctx, const __nv_bfloat16* ptr, int rows, int64_t ld, CUtensorMap* out) {
-    struct Entry { const void* ptr; int rows; int64_t ld; CUtensorMap map; };
-    static Entry cache[8];
+static int fa_map(tw_ctx* ctx, const __nv_bfloat16* ptr, int rows, int64_t ld, CUtensorMap* out, int box_rows = 128) {
+    struct Entry { const void* ptr; int rows; int64_t ld; int box_rows; CUtensorMap map; };
+    static Entry cache[16];
     static int n_cached = 0, next = 0;
     for (int i = 0; i < n_cached; ++i)
-        if (cache[i].ptr == ptr && cache[i].rows == rows && cache[i].ld == ld) { *out = cache[i].map; return TW_OK; }
+        if (cache[i].ptr == ptr && cache[i].rows == rows && cache[i].ld == ld && cache[i].box_rows == box_rows) { *out = cache[i].map; return TW_OK; }
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8)) {
         ctx->set_error(TW_E_UNSUPPORTED, "attention_tc: operands must be 16-byte aligned with a row pitch that is a multiple of 8 elements");
         return TW_E_UNSUPPORTED;
@@ -408,7 +1007,7 @@ static int fa_map(tw_ctx* ctx, const __nv_bfloat16* ptr, int rows, int64_t ld, C
     CUtensorMap m;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {64, 128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = g_fa_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -418,9 +1017,9 @@ static int fa_map(tw_ctx* ctx, const __nv_bfloat16* ptr, int rows, int64_t ld, C
         return TW_E_CUDA;
     }
     Entry& e = cache[next];
-    e.ptr = ptr; e.rows = rows; e.ld = ld; e.map = m;
-    next = (next + 1) % 8;
-    if (n_cached < 8) ++n_cached;
+    e.ptr = ptr; e.rows = rows; e.ld = ld; e.box_rows = box_rows; e.map = m;
+    next = (next + 1) % 16;
+    if (n_cached < 16) ++n_cached;
     *out = m;
     return TW_OK;
 }
@@ -440,17 +1039,23 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
         g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
         TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
         TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
     }
     if (causal && Sq != Sk) {
         ctx->set_error(TW_E_INVALID, "attention_tc: the causal mask needs as many queries as keys");
         return TW_E_INVALID;
     }
+    static const int variant = getenv("TWB200_FA_VARIANT") ? atoi(getenv("TWB200_FA_VARIANT")) : 3;
     CUtensorMap mq, mkv;
     TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
-    TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv));
+    TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, variant == 3 ? FA3_BK : 128));
     dim3 grid(ceil_div(Sq, FA_BQ), H, B);
-    static const int variant = getenv("TWB200_FA_VARIANT") ? atoi(getenv("TWB200_FA_VARIANT")) : 1;
-    if (variant == 0)
+    if (variant == 3)
+        encoder_attention_tc3_kernel<<<grid, FA_THREADS, FA3_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
+    else if (variant == 2)
+        encoder_attention_tc2_kernel<<<grid, FA_THREADS, FA2_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
+    else if (variant == 0)
         encoder_attention_tc_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
     else
         encoder_attention_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);

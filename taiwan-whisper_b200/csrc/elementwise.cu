@@ -129,9 +129,12 @@ template void layernorm<__nv_bfloat16>(const float*, const float*, const float*,
 // reads are contiguous in t, writes contiguous in c.
 template <typename T>
 __global__ void __launch_bounds__(256)
-im2col_conv1_kernel(const float* __restrict__ mel, T* __restrict__ out, int n_mel) {
+im2col_conv1_kernel(const float* __restrict__ mel, T* __restrict__ out, int n_mel, const float* __restrict__ clip_max) {
     __shared__ float tile[32][33 + 2];      // [c][t - t0 + 1], halo of 1 each side
     const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    // clip_max given: mel holds the un-normalised log10 values of the log-mel kernel's first pass; the per-clip floor and
+    // the (x + 4) / 4 scaling of logmel_finalize are applied on the way in (the conv padding stays exactly 0)
+    const float floor_v = clip_max ? clip_max[b] - 8.0f : 0.0f;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const float* src = mel + (int64_t)b * n_mel * TW_N_FRAMES;
     for (int cc = ty; cc < 32; cc += 8) {
@@ -139,7 +142,10 @@ im2col_conv1_kernel(const float* __restrict__ mel, T* __restrict__ out, int n_me
         for (int tt = tx; tt < 34; tt += 32) {
             const int t = t0 + tt - 1;
             float v = 0.0f;
-            if (c < n_mel && t >= 0 && t < TW_N_FRAMES) v = src[(int64_t)c * TW_N_FRAMES + t];
+            if (c < n_mel && t >= 0 && t < TW_N_FRAMES) {
+                v = src[(int64_t)c * TW_N_FRAMES + t];
+                if (clip_max) v = (fmaxf(v, floor_v) + 4.0f) * 0.25f;
+            }
             tile[cc][tt] = v;
         }
     }
@@ -158,12 +164,12 @@ im2col_conv1_kernel(const float* __restrict__ mel, T* __restrict__ out, int n_me
 }
 
 template <typename T>
-void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st) {
+void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st, const float* clip_max) {
     dim3 grid(ceil_div(TW_N_FRAMES, 32), ceil_div(n_mel, 32), B);
-    im2col_conv1_kernel<T><<<grid, 256, 0, st>>>(mel, out, n_mel);
+    im2col_conv1_kernel<T><<<grid, 256, 0, st>>>(mel, out, n_mel, clip_max);
 }
-template void im2col_conv1<float>(const float*, float*, int, int, cudaStream_t);
-template void im2col_conv1<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, cudaStream_t);
+template void im2col_conv1<float>(const float*, float*, int, int, cudaStream_t, const float*);
+template void im2col_conv1<__nv_bfloat16>(const float*, __nv_bfloat16*, int, int, cudaStream_t, const float*);
 
 // ---- conv2 im2col (stride 2, pad 1): out[(b,t')][tap*d + c] = h0[(b, 2t'+tap-1)][c]; 16-byte copies
 template <typename T>

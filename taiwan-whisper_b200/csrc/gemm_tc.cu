@@ -73,7 +73,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
     const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = (N + BN - 1) / BN;
     // a work item = (output tile, K split): split-K (ksplit > 1) is used by the residual-add epilogue of the skinny
     // decode GEMMs, whose partial sums are combined with fp32 atomics
@@ -149,40 +149,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TC_BM, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this buffer
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues: tc_ptx.cuh) =====================
+        constexpr uint32_t idesc = make_idesc(TC_BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);     // epilogue has drained this buffer
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (BN * Cfg::NACC);
+            const int ks = tile % ksplit;
+            const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+            int kstep = 0;                          // K steps issued for this tile
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                if (it == 0 && kb == kb0 && lane == 0) TW_TRACE(2);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (BN * Cfg::NACC);
-                const int ks = tile % ksplit;
-                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
-                int kstep = 0;                          // K steps issued for this tile
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase);
-                    if (it == 0 && kb == kb0) TW_TRACE(2);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                if (elect_one_sync()) {
                     const uint64_t a_desc = make_sw128_desc(sa);
                     const uint64_t b_desc = make_sw128_desc(sa + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k, ++kstep) {
+                    for (int k = 0; k < TC_BK / 16; ++k) {
                         // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
-                        const int a_idx = kstep % Cfg::NACC;
-                        tc_mma_f16(d_tmem + a_idx * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kstep >= Cfg::NACC) ? 1u : 0u);
+                        const int a_idx = (kstep + k) % Cfg::NACC;
+                        tc_mma_f16(d_tmem + a_idx * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kstep + k >= Cfg::NACC) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb + 1 == kb1) tc_commit(smem_u32(&tmem_full[acc]));      // accumulator ready
                 }
-                tc_commit(smem_u32(&tmem_full[acc]));                      // accumulator ready
-                TW_TRACE(3);
+                __syncwarp();
+                kstep += TC_BK / 16;
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (lane == 0) TW_TRACE(3);
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================

@@ -58,7 +58,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
     const int tiles_n = (N + BN - 1) / BN;
     const int num_tiles = tiles_n * ksplit;                     // one M tile
     const int k_blocks_total = K / 64;                          // K % 64 == 0 (checked by the launcher)
@@ -89,63 +89,67 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            // weights of the first work item do not depend on the previous kernel: stream them before the dependency wait
-            int prefetched = 0;
-            if ((int)blockIdx.x < num_tiles) {
-                const int ks = blockIdx.x % ksplit, n_blk = blockIdx.x / ksplit;
-                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
-                const int n_stage = (kb1 - kb0 + SK2_KSUB - 1) / SK2_KSUB;
-                prefetched = min(Cfg::STAGES, n_stage);
+        // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+        // weights of the first work item do not depend on the previous kernel: stream them before the dependency wait
+        int prefetched = 0;
+        if ((int)blockIdx.x < num_tiles) {
+            const int ks = blockIdx.x % ksplit, n_blk = blockIdx.x / ksplit;
+            const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+            const int n_stage = (kb1 - kb0 + SK2_KSUB - 1) / SK2_KSUB;
+            prefetched = min(Cfg::STAGES, n_stage);
+            if (elect_one_sync()) {
                 for (int i = 0; i < prefetched; ++i) {
                     const uint32_t fb = smem_u32(&full_bar[i]);
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                     tma_load_3d(&map_w, fb, smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_REGION, 0, n_blk * BN, kb0 + i * SK2_KSUB);
                 }
             }
-            pdl_wait();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int ks = tile % ksplit, n_blk = tile / ksplit;
-                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
-                for (int kb = kb0; kb < kb1; kb += SK2_KSUB) {
-                    const uint32_t fb = smem_u32(&full_bar[stage]);
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    if (prefetched > 0) {
-                        --prefetched;
-                        tma_load_3d(&map_a, fb, sa, 0, 0, kb);
-                    } else {
-                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            __syncwarp();
+        }
+        pdl_wait();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int ks = tile % ksplit, n_blk = tile / ksplit;
+            const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; kb += SK2_KSUB) {
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                if (prefetched > 0) {
+                    --prefetched;
+                    if (elect_one_sync()) tma_load_3d(&map_a, fb, sa, 0, 0, kb);
+                } else {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                    if (elect_one_sync()) {
                         mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                         tma_load_3d(&map_a, fb, sa, 0, 0, kb);
                         tma_load_3d(&map_w, fb, sa + Cfg::A_REGION, 0, n_blk * BN, kb);
                     }
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = make_idesc(128, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            const int ks = tile % ksplit;
+            const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; kb += SK2_KSUB) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                const int ks = tile % ksplit;
-                const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
-                for (int kb = kb0; kb < kb1; kb += SK2_KSUB) {
-                    mbar_wait(smem_u32(&full_bar[stage]), phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const int nsub = min(SK2_KSUB, kb1 - kb);      // K blocks of this stage that belong to the split
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const int nsub = min(SK2_KSUB, kb1 - kb);      // K blocks of this stage that belong to the split
+                if (elect_one_sync()) {
                     for (int j = 0; j < nsub; ++j) {
                         const uint64_t a_desc = make_sw128_desc(sa + j * Cfg::A_SUB);
                         const uint64_t b_desc = make_sw128_desc(sa + Cfg::A_REGION + j * Cfg::W_SUB);
@@ -154,9 +158,10 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb0 || j > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(smem_u32(&empty_bar[stage]));
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb + SK2_KSUB >= kb1) tc_commit(smem_u32(&tmem_full[acc]));
                 }
-                tc_commit(smem_u32(&tmem_full[acc]));
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {

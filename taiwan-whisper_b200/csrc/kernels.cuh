@@ -7,8 +7,10 @@ namespace tw {
 // ---- log-mel (logmel.cu)
 int logmel_init(tw_ctx* ctx);
 void logmel_destroy(tw_ctx* ctx);
+// finalize = false: stop after the first pass — `out` holds log10(max(mel, 1e-10)) and *clip_max_out the device array of
+// per-clip maxima; the caller applies max(x, clipmax - 8) and (x + 4) / 4 itself (the conv-stem im2col of the fused path)
 int logmel_run(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B, int n_mel,
-               float* out, cudaStream_t st);
+               float* out, cudaStream_t st, bool finalize = true, const float** clip_max_out = nullptr);
 
 // ---- GEMM  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)   (torch Linear layout)
 enum Epi {
@@ -66,9 +68,10 @@ __host__ __device__ __forceinline__ int64_t kv_page_row(const int32_t* page_tabl
 // ---- elementwise / normalisation (elementwise.cu)
 template <typename T>
 void layernorm(const float* x, const float* gamma, const float* beta, T* out, int M, int d, cudaStream_t st);
-// mel f32 [B,n_mel,3000] -> A1 T [B*3000, 3*n_mel], column = tap*n_mel + channel (pad 1)
+// mel f32 [B,n_mel,3000] -> A1 T [B*3000, 3*n_mel], column = tap*n_mel + channel (pad 1); clip_max (optional, [B]): mel is
+// the first-pass output of the log-mel kernel and the per-clip floor + scaling are applied here
 template <typename T>
-void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st);
+void im2col_conv1(const float* mel, T* out, int B, int n_mel, cudaStream_t st, const float* clip_max = nullptr);
 // h0 T [B*3000, d] -> A2 T [B*1500, 3*d], column = tap*d + channel (stride 2, pad 1)
 template <typename T>
 void im2col_conv2(const T* h0, T* out, int B, int d, cudaStream_t st);

@@ -15,6 +15,7 @@
 // ref: training/flax/distil_whisper/pipeline.py:40-58; filterbank from
 // transformers/audio_utils.py:263-333,356-375,453-545 (slaney scale, slaney norm, 0-8000 Hz).
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -22,11 +23,16 @@
 
 namespace tw {
 
-constexpr int LM_FR = 32;        // frames per CTA
 constexpr int LM_THREADS = 256;
 constexpr int LM_NFFT = 400;
 constexpr int LM_HOP = 160;
-constexpr int LM_NX = LM_FR * LM_HOP + (LM_NFFT - LM_HOP);   // 5360 staged samples
+// FR = frames per tile.  32: 2 CTAs / SM (109 KB); 16: the power spectrum re-uses the sample staging buffer and the CTA
+// shrinks to ~49 KB, so 3 CTAs (24 warps) fit an SM — the kernel is bound by issue slots and dependency stalls
+// (profiles/r02_logmel_ncu.md), which more resident warps hide
+template <int FR> struct LmCfg {
+    static constexpr int NX = FR * LM_HOP + (LM_NFFT - LM_HOP);   // staged samples (5360 for 32 frames)
+    static constexpr int CTAS = FR == 32 ? 2 : 3;
+};
 constexpr int LM_NBIN = 201;
 constexpr int LM_MAX_NNZ = 1024;
 
@@ -106,10 +112,11 @@ template <typename SampleT> __device__ __forceinline__ float sample_to_f32(Sampl
 template <> __device__ __forceinline__ float sample_to_f32<int16_t>(int16_t v) { return (float)v * (1.0f / 32768.0f); }
 template <> __device__ __forceinline__ float sample_to_f32<float>(float v) { return v; }
 
-struct LmSmem {
-    float x[LM_NX + 16];
-    float2 z[LM_FR][200];
-    float pw[LM_FR][LM_NBIN];
+template <int FR> struct LmSmem {
+    static constexpr int XPW = (LmCfg<FR>::NX + 16) > FR * LM_NBIN ? (LmCfg<FR>::NX + 16) : FR * LM_NBIN;
+    // staged samples x[NX] (stage 0-1) and the power spectrum pw[FR][201] (stage 3-4) share one buffer for FR = 16
+    float xpw[FR == 32 ? (LmCfg<FR>::NX + 16) + FR * LM_NBIN : XPW];
+    float2 z[FR][200];
     float win[LM_NFFT];
     float2 w200[200];
     float2 w400[LM_NBIN];
@@ -119,14 +126,17 @@ struct LmSmem {
     float red[LM_THREADS / 32];
 };
 
-template <typename SampleT>
-__global__ void __launch_bounds__(LM_THREADS, 2)
+template <typename SampleT, int LM_FR>
+__global__ void __launch_bounds__(LM_THREADS, LmCfg<LM_FR>::CTAS)
 logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t* __restrict__ n_valid_arr, int B,
               int n_mel, const int* __restrict__ fb_start, const int* __restrict__ fb_count,
               const int* __restrict__ fb_off, const float* __restrict__ fb_w, int fb_nnz,
               float* __restrict__ out, float* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    LmSmem& s = *reinterpret_cast<LmSmem*>(smem_raw);
+    constexpr int LM_NX = LmCfg<LM_FR>::NX;
+    LmSmem<LM_FR>& s = *reinterpret_cast<LmSmem<LM_FR>*>(smem_raw);
+    float* const sx = s.xpw;                                                           // staged samples
+    float (*const spw)[LM_NBIN] = reinterpret_cast<float (*)[LM_NBIN]>(LM_FR == 32 ? s.xpw + LM_NX + 16 : s.xpw);   // power spectrum
     const int tid = threadIdx.x;
 
     // ---- tables -> smem, once per (persistent) CTA
@@ -169,7 +179,7 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
             const int4 raw = __ldg(reinterpret_cast<const int4*>(x + j0));
             const SampleT* e = reinterpret_cast<const SampleT*>(&raw);
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) s.x[i0 + q] = sample_to_f32<SampleT>(e[q]);
+            for (int q = 0; q < VEC; ++q) sx[i0 + q] = sample_to_f32<SampleT>(e[q]);
         } else {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) {
@@ -178,7 +188,7 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
                 else if (j >= TW_N_SAMPLES) j = 2 * (TW_N_SAMPLES - 1) - j;
                 float val = 0.0f;
                 if (j >= 0 && j < n_valid) val = sample_to_f32<SampleT>(x[j]);
-                s.x[i0 + q] = val;
+                sx[i0 + q] = val;
             }
         }
     }
@@ -191,7 +201,7 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
             const int n = 25 * n1 + n2;
-            const float2 xv = *reinterpret_cast<const float2*>(&s.x[LM_HOP * f + 2 * n]);
+            const float2 xv = *reinterpret_cast<const float2*>(&sx[LM_HOP * f + 2 * n]);
             const float2 wv = *reinterpret_cast<const float2*>(&s.win[2 * n]);
             v[n1] = {xv.x * wv.x, xv.y * wv.y};
         }
@@ -241,20 +251,20 @@ logmel_kernel(const SampleT* __restrict__ pcm, int64_t pcm_stride, const int32_t
         const float2 w = s.w400[k];
         const float tr = w.x * orr - w.y * oi, ti = w.x * oi + w.y * orr;
         const float ar = er + tr, ai = ei + ti, br = er - tr, bi = ei - ti;
-        s.pw[f][k] = ar * ar + ai * ai;
-        s.pw[f][200 - k] = br * br + bi * bi;        // k = 100 writes the same value twice
+        spw[f][k] = ar * ar + ai * ai;
+        spw[f][200 - k] = br * br + bi * bi;        // k = 100 writes the same value twice
     }
     __syncthreads();
 
-    // ---- sparse mel filterbank + log10 clamp; thread -> (frame = tid%32, mel = tid/32 + 8 it)
-    const int f = tid & 31;
+    // ---- sparse mel filterbank + log10 clamp; thread -> (frame = tid % FR, mel = tid / FR + (256 / FR) it)
+    const int f = tid % LM_FR;
     const int frame = f0 + f;
     float lmax = -INFINITY;
     float* out_b = out + (int64_t)b * n_mel * TW_N_FRAMES;
-    for (int m = tid >> 5; m < n_mel; m += LM_THREADS / 32) {
+    for (int m = tid / LM_FR; m < n_mel; m += LM_THREADS / LM_FR) {
         const int st = s.fb_start[m], cnt = s.fb_count[m], off = s.fb_off[m];
         float acc = 0.0f;
-        for (int j = 0; j < cnt; ++j) acc = fmaf(s.fbw[off + j], s.pw[f][st + j], acc);
+        for (int j = 0; j < cnt; ++j) acc = fmaf(s.fbw[off + j], spw[f][st + j], acc);
         const float lv = __log10f(fmaxf(acc, 1e-10f));      // MUFU.LG2 path: |err| ~1e-7, the contract is 1e-4
         if (frame < TW_N_FRAMES) {
             out_b[(int64_t)m * TW_N_FRAMES + frame] = lv;
@@ -358,8 +368,10 @@ int logmel_init(tw_ctx* ctx) {
     TW_CUDA_OK(ctx, cudaMemcpyToSymbol(g_tables, &h, sizeof(h)));
     TW_CHECK(build_bank(ctx, ctx->banks[0], 80));
     TW_CHECK(build_bank(ctx, ctx->banks[1], 128));
-    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem)));
-    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem)));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<int16_t, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem<32>)));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem<32>)));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<int16_t, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem<16>)));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(logmel_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem<16>)));
     return TW_OK;
 }
 
@@ -374,7 +386,7 @@ void logmel_destroy(tw_ctx* ctx) {
 }
 
 int logmel_run(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, const int32_t* n_valid, int B, int n_mel,
-               float* out, cudaStream_t st) {
+               float* out, cudaStream_t st, bool finalize, const float** clip_max_out) {
     if (B <= 0) return TW_OK;
     if (n_mel != 80 && n_mel != 128) {
         ctx->set_error(TW_E_INVALID, "tw_logmel: n_mel must be 80 or 128");
@@ -396,20 +408,30 @@ int logmel_run(tw_ctx* ctx, const void* pcm, int pcm_dtype, int64_t pcm_stride, 
     }
     const tw_ctx::MelBank& bank = ctx->banks[n_mel == 80 ? 0 : 1];
     logmel_init_max<<<ceil_div(B, 256), 256, 0, st>>>(ctx->d_clip_max, B);
-    const int n_tiles = ceil_div(TW_N_FRAMES, LM_FR) * B;
-    const int grid = n_tiles < 2 * ctx->sm_count ? n_tiles : 2 * ctx->sm_count;      // persistent: 2 CTAs per SM
-    if (pcm_dtype == TW_I16)
-        logmel_kernel<int16_t><<<grid, LM_THREADS, sizeof(LmSmem), st>>>(
-            (const int16_t*)pcm, pcm_stride, n_valid, B, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
-            bank.nnz, out, ctx->d_clip_max);
-    else
-        logmel_kernel<float><<<grid, LM_THREADS, sizeof(LmSmem), st>>>(
-            (const float*)pcm, pcm_stride, n_valid, B, n_mel, bank.d_start, bank.d_count, bank.d_offset, bank.d_w,
-            bank.nnz, out, ctx->d_clip_max);
-    const int per_clip4 = n_mel * TW_N_FRAMES / 4;
-    dim3 g2(ceil_div(per_clip4, 256 * 4), B);
-    logmel_finalize<<<g2, 256, 0, st>>>(out, ctx->d_clip_max, per_clip4);
-    ctx->launches += 3;
+    static const int fr = getenv("TWB200_LM_FR") ? atoi(getenv("TWB200_LM_FR")) : 16;      // tuning knob: frames per tile (16 | 32)
+#define TW_LM_LAUNCH(ST, FR)                                                                                                   \
+    do {                                                                                                                       \
+        const int n_tiles = ceil_div(TW_N_FRAMES, FR) * B;                                                                     \
+        const int per_sm = LmCfg<FR>::CTAS;                                                                                    \
+        const int grid = n_tiles < per_sm * ctx->sm_count ? n_tiles : per_sm * ctx->sm_count;                                  \
+        logmel_kernel<ST, FR><<<grid, LM_THREADS, sizeof(LmSmem<FR>), st>>>((const ST*)pcm, pcm_stride, n_valid, B, n_mel, bank.d_start, \
+                                                                             bank.d_count, bank.d_offset, bank.d_w, bank.nnz, out,        \
+                                                                             ctx->d_clip_max);                                           \
+    } while (0)
+    if (pcm_dtype == TW_I16) {
+        if (fr == 32) TW_LM_LAUNCH(int16_t, 32); else TW_LM_LAUNCH(int16_t, 16);
+    } else {
+        if (fr == 32) TW_LM_LAUNCH(float, 32); else TW_LM_LAUNCH(float, 16);
+    }
+#undef TW_LM_LAUNCH
+    if (clip_max_out) *clip_max_out = ctx->d_clip_max;
+    if (finalize) {
+        const int per_clip4 = n_mel * TW_N_FRAMES / 4;
+        dim3 g2(ceil_div(per_clip4, 256 * 4), B);
+        logmel_finalize<<<g2, 256, 0, st>>>(out, ctx->d_clip_max, per_clip4);
+        ctx->launches += 1;
+    }
+    ctx->launches += 2;
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

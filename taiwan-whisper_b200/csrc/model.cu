@@ -411,14 +411,15 @@ inline GemmEpi mk_epi(int mode, const float* bias, void* C, int64_t ldc, const f
 }
 
 template <typename T>
-int encode_impl(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, cudaStream_t st) {
+int encode_impl(tw_model* m, const float* mel, int B, void* enc_out, int tap_layer, float* tap_out, cudaStream_t st,
+                const float* mel_clip_max = nullptr) {
     const tw_model_desc& D = m->desc;
     const int d = D.d_model, M = B * TW_N_CTX, M0 = B * TW_N_FRAMES, K1 = 3 * D.n_mel;
     tw_ctx* ctx = m->ctx;
     T* a1 = (T*)m->ws_a1; T* h0 = (T*)m->ws_h0; T* a2 = (T*)m->ws_a2qkv; T* qkv = (T*)m->ws_a2qkv;
     T* xn = (T*)m->ws_xn; T* att = (T*)m->ws_att; T* hmid = (T*)m->ws_hmid;
     float* x = m->ws_x;
-    im2col_conv1<T>(mel, a1, B, D.n_mel, st);
+    im2col_conv1<T>(mel, a1, B, D.n_mel, st, mel_clip_max);
     TW_CHECK(gemm<T>(m, a1, K1, (const T*)m->conv1_w, K1, M0, d, K1, mk_epi(EPI_GELU, m->conv1_b, h0, d), st));
     im2col_conv2<T>(h0, a2, B, d, st);
     TW_CHECK(gemm<T>(m, a2, 3 * d, (const T*)m->conv2_w, 3 * d, M, d, 3 * d,
@@ -1016,10 +1017,12 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
         nv = m->ws_nvalid;
     }
     cudaEventRecord(m->ev[0], st);
-    TW_CHECK(logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st));
+    // the per-clip floor and scaling of the log-mel (its second pass) ride in the conv-stem im2col
+    const float* clip_max = nullptr;
+    TW_CHECK(logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st, false, &clip_max));
     cudaEventRecord(m->ev[1], st);
-    int r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st)
-                               : encode_impl<float>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st);
+    int r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st, clip_max)
+                               : encode_impl<float>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st, clip_max);
     if (r != TW_OK) return r;
     cudaEventRecord(m->ev[2], st);
     r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, m->ws_enc, B, st) : cross_kv_impl<float>(m, m->ws_enc, B, st);

@@ -10,6 +10,16 @@ namespace tw {
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp (deterministic for a given mask).  The single-thread roles (MMA issuer, TMA producer)
+// run their loops with ALL lanes and issue under `if (elect_one_sync())`: control flow stays warp-uniform, so descriptors and
+// barrier addresses live in uniform registers and consecutive tcgen05.mma / TMA instructions issue back to back.  Under
+// `if (lane == 0)` the compiler wraps every uniform-datapath instruction in a divergence loop (ELECT / BRA.U.ANY, tens of
+// cycles each) — measured as the per-MMA issue cost that paced the skinny GEMMs and the attention kernel (profiles/r02_*).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
+    return pred;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }

@@ -25,3 +25,24 @@ def prompt_ids(vocab, timestamps=False, language="zh"):
     if not timestamps:
         p.append(ids.notimestamps)
     return p
+
+
+class StubWhisperTokenizer:
+    """Duck-typed tokenizer for HF's module-level `_decode_asr` (needs no vocabulary files): text of a token list is the
+    comma-joined ids, so the chunks' token lists can be read back."""
+
+    def __init__(self, ids):
+        self.ids = ids
+        self.all_special_ids = list(range(ids.eos, ids.timestamp_begin))
+
+    def convert_tokens_to_ids(self, tok):
+        return {"<|notimestamps|>": self.ids.notimestamps, "<|startofprev|>": self.ids.startofprev,
+                "<|startoftranscript|>": self.ids.sot}[tok]
+
+    def _strip_prompt(self, token_ids, prompt_token_id, decoder_start_token_id):
+        if token_ids and token_ids[0] == prompt_token_id:
+            return token_ids[token_ids.index(decoder_start_token_id):] if decoder_start_token_id in token_ids else []
+        return token_ids
+
+    def decode(self, ids):
+        return "".join(f"{int(t)}," for t in ids)

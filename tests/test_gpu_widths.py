@@ -294,20 +294,36 @@ def test_row_budgets_prefix_property_benched_width(dtype_name):
         full, full_len = m.decode(enc, P, max_length, False)
         full = full.cpu().numpy()
         assert (full_len.cpu().numpy() == n_gen).all()
+        # bf16: the K|V stream splits its rows over the CTAs by the number of active clips, so partial sums merge in another
+        # order once a clip has finished and a free-running row can take the other side of a near-tie (and then diverges for
+        # good).  The prefix property is therefore checked teacher-forced in bf16 (the unconstrained run's ids are fed back),
+        # exactly (free-running) in fp32 check mode.
+        forced = None if dtype_name == "f32" else torch.from_numpy(full.astype(np.int32))
+        if forced is not None:
+            base, _ = m.decode(enc, P, max_length, False, forced=forced)
+            base = base.cpu().numpy()
+        else:
+            base = full
         for bud in (budgets, np.minimum(budgets, 40)):
             m.set_row_budgets(bud.tolist())
             for call in range(2):
-                toks, lens = m.decode(enc, P, max_length, False)
+                toks, lens = m.decode(enc, P, max_length, False, forced=forced)
                 toks, lens = toks.cpu().numpy(), lens.cpu().numpy()
                 assert lens.tolist() == bud.tolist()
                 bad = 0
                 for b in range(B):
                     assert (toks[b, bud[b]:] == ids.pad).all(), b
-                    bad += int((toks[b, :bud[b]] != full[b, :bud[b]]).sum())
+                    bad += int((toks[b, :bud[b]] != base[b, :bud[b]]).sum())
                 if dtype_name == "f32":
                     assert bad == 0
-                else:           # bf16: split-K atomics make near-ties order-dependent; free-running rows may then diverge
-                    assert bad <= 0.02 * bud.sum(), (bad, int(bud.sum()))
+                else:
+                    assert bad <= 0.005 * bud.sum(), (bad, int(bud.sum()))
+                if forced is not None and call == 0:        # the production (graph-replayed) bf16 step with budgets: structure only
+                    ft, fl = m.decode(enc, P, max_length, False)
+                    ft, fl = ft.cpu().numpy(), fl.cpu().numpy()
+                    assert fl.tolist() == bud.tolist()
+                    for b in range(B):
+                        assert (ft[b, bud[b]:] == ids.pad).all() and (ft[b, :bud[b]] < sh.vocab).all()
             m.set_row_budgets(None)
         again, _ = m.decode(enc, P, max_length, False)
         if dtype_name == "f32":
@@ -398,3 +414,44 @@ def test_call_site_replay_validator_and_pseudo_labelling():
     finally:
         m5.close()
         m445.close()
+
+
+def test_longform_config5_end_to_end():
+    """Config 5 end to end on one recording (75 s -> 4 windows of 30 s, hop 20 s): every window's timestamp-mode ids equal the
+    oracle's on the zero-padded window (fp32 check mode), and the stitched chunks equal HF `_decode_asr(...,
+    return_timestamps=True)` on those per-window ids (ref training/flax/distil_whisper/pipeline.py:353-375)."""
+    _cuda()
+    import torch as _t
+    from transformers.models.whisper.tokenization_whisper import _decode_asr
+    from oracle import hf_ref, logmel_np, whisper_np
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration
+    from taiwan_whisper_b200.longform import chunk_plan, transcribe_longform
+    from taiwan_whisper_b200.synth import dequantise, synth_batch
+    from tests.helpers import StubWhisperTokenizer
+    sh = SHAPES["tiny"]
+    tid = token_ids(sh.vocab)
+    hf = hf_ref.build_hf_model(sh, seed=1234)
+    W = weights_np(hf)
+    rec = np.concatenate(list(synth_batch(0, 3)))[: 16000 * 75]
+    max_length = 40
+    m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.float32, max_batch=3, output_layout="5.x")     # 4 windows: two batches
+    try:
+        tok = StubWhisperTokenizer(tid)
+        chunks = transcribe_longform(m, torch.from_numpy(rec).cuda(), max_length=max_length, special_ids=tok.all_special_ids)
+    finally:
+        m.close()
+    starts, strides = chunk_plan(len(rec))
+    assert len(starts) == 4 and strides[0][1] == 0 and strides[-1][2] == 0
+    P, rules = prompt_ids(sh.vocab, True), default_rules(sh.vocab, True)
+    outs = []
+    for s0, st in zip(starts, strides):
+        win = np.zeros(480000, np.int16)
+        win[: st[0]] = rec[s0:s0 + st[0]]
+        mel = logmel_np.log_mel(dequantise(win[None]), sh.n_mel)[0]
+        ids = whisper_np.greedy_decode(W, whisper_np.encoder_forward(W, mel, sh.heads, sh.enc_layers), P, rules, max_length, sh.heads,
+                                       sh.dec_layers)
+        outs.append({"tokens": _t.tensor([ids]), "stride": (st[0] / 16000, st[1] / 16000, st[2] / 16000)})
+    text, opt = _decode_asr(tok, outs, return_timestamps=True, return_language=False, time_precision=0.02)
+    assert [c["timestamp"] for c in chunks] == [c["timestamp"] for c in opt["chunks"]]
+    assert [tok.decode(c["tokens"]) for c in chunks] == [c["text"] for c in opt["chunks"]]
+    assert len(chunks) > 0

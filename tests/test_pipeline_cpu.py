@@ -104,23 +104,11 @@ def test_segments_properties_random_streams():
             assert ids and w0 <= s0 <= w0 + wl + 1e-9 and w0 <= s1 <= w0 + wl + 1e-9
 
 
-class _StubTokenizer:
-    """Duck-typed tokenizer for HF's module-level `_decode_asr` (needs no vocabulary files): text of a token list is the
-    comma-joined ids, so the chunks' token lists can be read back."""
+from tests.helpers import StubWhisperTokenizer
 
-    def __init__(self):
-        self.all_special_ids = list(range(EOS, TSB))
 
-    def convert_tokens_to_ids(self, tok):
-        return {"<|notimestamps|>": IDS.notimestamps, "<|startofprev|>": IDS.startofprev, "<|startoftranscript|>": IDS.sot}[tok]
-
-    def _strip_prompt(self, token_ids, prompt_token_id, decoder_start_token_id):
-        if token_ids and token_ids[0] == prompt_token_id:
-            return token_ids[token_ids.index(decoder_start_token_id):] if decoder_start_token_id in token_ids else []
-        return token_ids
-
-    def decode(self, ids):
-        return "".join(f"{int(t)}," for t in ids)
+def _StubTokenizer():
+    return StubWhisperTokenizer(IDS)
 
 
 def _random_window_tokens(rng, t_lo, t_hi):
