@@ -2,19 +2,15 @@
 // head_dim 64, bf16 operands, fp32 accumulate / softmax.  (HF WhisperAttention.forward,
 // modeling_whisper.py:284-358; q is pre-scaled, no mask.)
 //
-// One CTA = one 128-query block of one (clip, head); two CTAs are co-resident per SM (256 TMEM columns,
-// ~112 KB shared memory each) so one CTA's softmax overlaps the other's MMAs.
-//   warp 4      TMA producer: Q tile once, then K / V tiles (128 keys x 64 dims, 128-byte swizzle) through
-//               2-deep rings, straight out of the fused QKV activation matrix [B*S, 3d]
-//   warp 5      MMA issuer: S = Q K^T (tcgen05.mma M128 N128 K16 x4, both operands K-major) into TMEM columns
-//               [0,128); O_tile = P V (M128 N64 K16 x8, A = P from shared memory, B = V tile used MN-major)
-//               into TMEM columns [128,192)
-//   warps 0-3   softmax: thread = query row.  tcgen05.ld the scores, running max / sum in registers (no
-//               shuffles: a thread owns its row), P = exp2(s*log2e - m*log2e) rounded to bf16 and written to
-//               shared memory in the K-major 128-byte-swizzle layout the MMA expects, then O_reg = O_reg*scale
-//               + O_tile read back from TMEM.  Final O / l stored as bf16 (128 contiguous bytes per row).
-// Keys beyond the clip length (the 1536-padded tail, which TMA fills with the next clip's rows or zeros)
-// are masked to -inf before the softmax.
+// One CTA = one 128-query block of one (clip, head); two CTAs are co-resident per SM (208 of 256 TMEM columns,
+// ~90 KB shared memory each).
+//   warp 4      TMA producer: Q tile once, then K / V tiles (64 keys x 64 dims, 128-byte swizzle) through 4-deep rings,
+//               straight out of the fused QKV activation matrix [B*S, 3d]
+//   warp 5      MMA issuer (warp-uniform loop, one elected lane): S = Q K^T (M128 N64 K16 x4) into one of two TMEM score
+//               buffers; O += P V and L += P 1 with P read from TMEM (M128 N64 / N16, K16 x4, V used MN-major)
+//   warps 0-3   softmax: thread = query row; scores from TMEM to registers once, P back to TMEM — see the comment on the kernel
+// Keys beyond the clip length (the padded tail, which TMA fills with the next clip's rows or zeros) and, under the causal
+// mask, keys later than the query are given zero probability.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -22,10 +18,9 @@
 
 namespace tw {
 
-constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64;
+constexpr int FA_BQ = 128, FA_D = 64;
 constexpr int FA_THREADS = 192;
 constexpr int FA_TILE_BYTES = 128 * 64 * 2;      // one 128 x 64 bf16 tile = 16 KB
-constexpr int FA_SMEM = 1024 + FA_TILE_BYTES * (1 + 2 + 1 + 2) + 256;   // Q, K x2, V x1, P (2 atoms): 2 CTAs / SM
 constexpr int FA_TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t fa_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,315 +103,8 @@ __host__ __device__ constexpr uint32_t fa_idesc(int M, int N, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// VAR 1 (default): the TMEM load of the next 32 score columns is issued before the math of the current ones (+6 % on B200);
-// VAR 0 (TWB200_FA_VARIANT=0): one load at a time.  Measured and dropped (profiles/r01_encoder_attention_ncu.md): a lazy
-// running max (single pass over the scores), a share of the exponentials as an FMA-pipe polynomial, back-off in the
-// producer / MMA-issuer waits — none of them faster.
-template <int VAR>
-__global__ void __launch_bounds__(FA_THREADS, 2)
-encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                            __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
-    extern __shared__ unsigned char fa_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sQ = smem;
-    unsigned char* sK = smem + FA_TILE_BYTES;           // 2 stages
-    unsigned char* sV = smem + 3 * FA_TILE_BYTES;       // 1 stage (V(j) is only needed after softmax(j))
-    unsigned char* sP = smem + 4 * FA_TILE_BYTES;       // 2 swizzle atoms (keys 0-63 | 64-127), 128 rows each
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE_BYTES);
-    uint64_t* q_full = bars;          // 1
-    uint64_t* k_full = bars + 1;      // 2
-    uint64_t* k_empty = bars + 3;     // 2
-    uint64_t* v_full = bars + 5;      // 2
-    uint64_t* v_empty = bars + 7;     // 2
-    uint64_t* s_full = bars + 9;      // 1  QK^T done
-    uint64_t* p_full = bars + 10;     // 1  P written (and S consumed)
-    uint64_t* o_full = bars + 11;     // 1  PV done
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int d = H * FA_D;
-    const int q0 = qb * FA_BQ;
-    // S queries per clip (rows of map_q), Sk keys / values per clip (rows of map_kv); causal: key index <= query index, so
-    // query block qb only visits key tiles 0..qb (FA_BQ == FA_BK)
-    const int n_tiles = causal ? min((Sk + FA_BK - 1) / FA_BK, qb + 1) : (Sk + FA_BK - 1) / FA_BK;
-    const int row_base = b * S;                       // first query row of this clip
-    const int kv_base = b * Sk;                       // first key / value row of this clip
-
-    if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
-        fa_mbar_init(fa_smem_u32(q_full), 1);
-        for (int i = 0; i < 2; ++i) {
-            fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
-            fa_mbar_init(fa_smem_u32(&k_empty[i]), 1);
-            fa_mbar_init(fa_smem_u32(&v_full[i]), 1);
-            fa_mbar_init(fa_smem_u32(&v_empty[i]), 1);
-        }
-        fa_mbar_init(fa_smem_u32(s_full), 1);
-        fa_mbar_init(fa_smem_u32(p_full), 4);          // one arrive per softmax warp
-        fa_mbar_init(fa_smem_u32(o_full), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fa_smem_u32(tmem_ptr)), "r"(FA_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fa_fence_before();
-    __syncthreads();
-    fa_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S = tmem_base;            // columns [0,128)
-    const uint32_t tmem_O = tmem_base + 128;      // columns [128,192)
-
-    if (warp == 4) {
-        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-        if (fa_elect()) {
-            fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
-            fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
-        }
-        __syncwarp();
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
-            if (fa_elect()) {
-                fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), k_col0 + h * FA_D,
-                               kv_base + j * FA_BK);
-            }
-            __syncwarp();
-            fa_mbar_wait(fa_smem_u32(&v_empty[0]), (j & 1) ^ 1);
-            if (fa_elect()) {
-                fa_mbar_expect_tx(fa_smem_u32(&v_full[0]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[0]), fa_smem_u32(sV), v_col0 + h * FA_D, kv_base + j * FA_BK);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 5) {
-        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
-        constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
-        const uint32_t q_addr = fa_smem_u32(sQ), v_addr = fa_smem_u32(sV), p_addr = fa_smem_u32(sP);
-        auto issue_pv = [&](int j) {          // O_tile(j) = P(j) V(j): P is in shared memory since p_full(j)
-            fa_mbar_wait(fa_smem_u32(p_full), j & 1);
-            fa_mbar_wait(fa_smem_u32(&v_full[0]), j & 1);
-            fa_fence_after();
-            if (fa_elect()) {
-#pragma unroll
-                for (int k = 0; k < FA_BK / 16; ++k) {
-                    // A: P atom (k/4), 32-byte steps inside the 128-byte swizzle row; B: 16 key rows = 2048 bytes
-                    const uint64_t p_desc = fa_desc(p_addr + (k >> 2) * FA_TILE_BYTES) + 2 * (k & 3);
-                    const uint64_t v_desc = fa_desc(v_addr + k * 2048);
-                    fa_mma(tmem_O, p_desc, v_desc, idesc_pv, k > 0 ? 1u : 0u);
-                }
-                fa_commit(fa_smem_u32(&v_empty[0]));
-                fa_commit(fa_smem_u32(o_full));
-            }
-            __syncwarp();
-        };
-        fa_mbar_wait(fa_smem_u32(q_full), 0);
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            // S(j) = Q K(j)^T   (S columns are free: the softmax warps arrived on p_full(j-1))
-            fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
-            if (j > 0) fa_mbar_wait(fa_smem_u32(p_full), (j - 1) & 1);
-            fa_fence_after();
-            if (fa_elect()) {
-                const uint64_t q_desc = fa_desc(q_addr);
-                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                fa_commit(fa_smem_u32(&k_empty[st]));
-                fa_commit(fa_smem_u32(s_full));
-            }
-            __syncwarp();
-            if (j > 0) issue_pv(j - 1);
-        }
-        issue_pv(n_tiles - 1);
-    } else {
-        // ===================== softmax warps 0..3: thread = query row =====================
-        const int r = warp * 32 + lane;                 // row inside the tile == TMEM lane
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        const float LOG2E = 1.4426950408889634f;
-        float o_acc[FA_D];
-#pragma unroll
-        for (int i = 0; i < FA_D; ++i) o_acc[i] = 0.0f;
-        float m_run = -INFINITY, l_run = 0.0f, scale_prev = 1.0f;
-        // ---- the two passes over the 128 score columns of this row (TMEM lane), 32 columns at a time
-        // pass A: raw row max (masked columns excluded)
-        auto max_pass = [&](int valid, bool full_tile) -> float {
-            float mx = -INFINITY;
-            auto fold = [&](const uint32_t* v, int c) {
-                if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
-                }
-            };
-            if (VAR & 1) {
-                uint32_t va[32], vb[32];
-                fa_tmem_ld32(tmem_S + lane_off, va);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); fold(va, 0);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); fold(vb, 32);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); fold(va, 64);
-                fa_tmem_wait_ld(); fold(vb, 96);
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < FA_BK; c += 32) {
-                    uint32_t v[32];
-                    fa_tmem_ld32(tmem_S + lane_off + c, v);
-                    fa_tmem_wait_ld();
-                    fold(v, c);
-                }
-            }
-            return mx;
-        };
-        // pass B: P = exp2(s*log2e - m*log2e) -> bf16 -> shared memory (K-major, 128-byte swizzle); returns the row sum
-        auto exp_pass = [&](float mneg, int valid, bool full_tile) -> float {
-            float lsum0 = 0.0f, lsum1 = 0.0f;
-            auto chunk = [&](const uint32_t* v, int c) {
-                uint32_t pk[16];
-                if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        const float p0 = fa_ex2(fmaf(s0, LOG2E, mneg));
-                        const float p1 = fa_ex2(fmaf(s1, LOG2E, mneg));
-                        lsum0 += p0;
-                        lsum1 += p1;
-                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-                        const float p0 = fa_mask0(fa_ex2(fmaf(s0, LOG2E, mneg)), c + i, valid);
-                        const float p1 = fa_mask0(fa_ex2(fmaf(s1, LOG2E, mneg)), c + i + 1, valid);
-                        lsum0 += p0;
-                        lsum1 += p1;
-                        __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                    }
-                }
-                // 32 keys = 64 bytes = 4 chunks of 16 B; chunk index inside the 128-byte row: ((c % 64) / 8) + q
-                unsigned char* prow = sP + (c >> 6) * FA_TILE_BYTES + r * 128;
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    const int ch = ((c & 63) >> 3) + qd;
-                    *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) =
-                        make_uint4(pk[4 * qd], pk[4 * qd + 1], pk[4 * qd + 2], pk[4 * qd + 3]);
-                }
-            };
-            if (VAR & 1) {
-                uint32_t va[32], vb[32];
-                fa_tmem_ld32(tmem_S + lane_off, va);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); chunk(va, 0);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); chunk(vb, 32);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); chunk(va, 64);
-                fa_tmem_wait_ld(); chunk(vb, 96);
-            } else {
-#pragma unroll 1
-                for (int c = 0; c < FA_BK; c += 32) {
-                    uint32_t v[32];
-                    fa_tmem_ld32(tmem_S + lane_off + c, v);
-                    fa_tmem_wait_ld();
-                    chunk(v, c);
-                }
-            }
-            return lsum0 + lsum1;
-        };
-
-        for (int j = 0; j < n_tiles; ++j) {
-            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
-            fa_fence_after();
-            // keys >= valid are padding (the tail of the clip) or, under the causal mask, later than this row's query
-            const int valid = causal ? min(Sk - j * FA_BK, q0 + r - j * FA_BK + 1) : Sk - j * FA_BK;
-            // only the last key tile of a clip / the diagonal tile is masked (warp-uniform)
-            const bool full_tile = (Sk - j * FA_BK >= FA_BK) && !(causal && j == qb);
-            const float m_new = fmaxf(m_run, max_pass(valid, full_tile));
-            const float scale = fa_ex2((m_run - m_new) * LOG2E);    // 0 on the first tile (m_run = -inf)
-            // the previous P V must have finished reading P before it is overwritten, and O_tile(j-1) is folded in
-            if (j > 0) {
-                fa_mbar_wait(fa_smem_u32(o_full), (j - 1) & 1);
-                fa_fence_after();
-#pragma unroll
-                for (int c = 0; c < FA_D; c += 32) {
-                    uint32_t v[32];
-                    fa_tmem_ld32(tmem_O + lane_off + c, v);
-                    fa_tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], scale_prev, __uint_as_float(v[i]));
-                }
-            }
-            const float lsum = exp_pass(-m_new * LOG2E, valid, full_tile);
-            l_run = l_run * scale + lsum;
-            m_run = m_new;
-            scale_prev = scale;
-            // P visible to the tensor core (async proxy); S columns free again
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            fa_fence_before();
-            __syncwarp();
-            if (lane == 0) fa_mbar_arrive(fa_smem_u32(p_full));
-        }
-        // last O tile.  NB: scale_prev belongs to the tile whose P V is now finishing: O = O*scale + O_tile
-        fa_mbar_wait(fa_smem_u32(o_full), (n_tiles - 1) & 1);
-        fa_fence_after();
-#pragma unroll
-        for (int c = 0; c < FA_D; c += 32) {
-            uint32_t v[32];
-            fa_tmem_ld32(tmem_O + lane_off + c, v);
-            fa_tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], scale_prev, __uint_as_float(v[i]));
-        }
-        const int q = q0 + r;
-        if (q < S) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* orow = out + ((int64_t)(row_base + q)) * d + h * FA_D;
-#pragma unroll
-            for (int i = 0; i < FA_D; i += 8) {
-                uint4 pk;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(o_acc[i] * inv, o_acc[i + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(orow + i) = pk;
-            }
-        }
-        fa_fence_before();
-    }
-    __syncthreads();
-    if (warp == 5) {
-        fa_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
-    }
-}
-
-// =====================================================================================================================
-// v2 ("instruction diet", default): same roles and tile shapes, but the softmax warps execute ~3 instructions per score
-// instead of ~6 — the round-1 profile (profiles/r01_encoder_attention_ncu.md) showed the kernel bound by the issue slots
-// and dependency stalls of the one softmax warp per SM sub-partition, not by MUFU, tensor or memory throughput:
-//   * P (bf16) is written back to TENSOR MEMORY over the score columns it was computed from (tcgen05.st, 64 columns) and
-//     P V runs with the A operand in TMEM: no shared-memory P tile, no swizzled 16-byte stores, no proxy fence;
-//   * O accumulates in TMEM across key tiles (P V with accumulate) instead of being folded into registers every tile; the
-//     exponentials use a per-row REFERENCE max that is only moved when the tile max exceeds it by more than 2^8
-//     (then O and the row sum are rescaled in TMEM, warp-uniformly skipped otherwise) — exact, because numerator and
-//     denominator carry the same reference;
-//   * the row sum is produced by the tensor core: a second MMA of P against a tile of ones accumulates sum_k P[r,k] into a
-//     TMEM column, from the same bf16-rounded P the numerator uses (no FADD per score);
-//   * the row max uses the 3-input FMNMX.
-// MMA issue order per key tile is P V (j-1) then Q K^T (j): the tensor pipe executes in order, so Q K^T (j) overwrites the
-// score / P columns only after P V (j-1) has read them, and s_full(j) implies that P V (j-1) has completed.
-constexpr int FA2_SMEM = 1024 + FA_TILE_BYTES * (1 + 2 + 2 + 1) + 256;    // Q, K x2, V x2, ones: 2 CTAs / SM
-constexpr float FA2_RESCALE_LOG2 = 8.0f;
+// ---- tensor-memory helpers of the kernel below: P V with the A operand in TMEM, tcgen05.st, 3-input max
+constexpr float FA2_RESCALE_LOG2 = 8.0f;      // the reference max of a row moves only when the tile max exceeds it by 2^8
 
 __device__ __forceinline__ void fa_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -455,278 +143,33 @@ __device__ __forceinline__ float fa_max3(float a, float b, float c) {
     return d;
 }
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
-encoder_attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                             __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
-    extern __shared__ unsigned char fa_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sQ = smem;
-    unsigned char* sK = smem + FA_TILE_BYTES;           // 2 stages
-    unsigned char* sV = smem + 3 * FA_TILE_BYTES;       // 2 stages
-    unsigned char* sOne = smem + 5 * FA_TILE_BYTES;     // 128 x 64 bf16 ones (B operand of the row-sum MMA; any layout reads as ones)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * FA_TILE_BYTES);
-    uint64_t* q_full = bars;          // 1
-    uint64_t* k_full = bars + 1;      // 2
-    uint64_t* k_empty = bars + 3;     // 2
-    uint64_t* v_full = bars + 5;      // 2
-    uint64_t* v_empty = bars + 7;     // 2
-    uint64_t* s_full = bars + 9;      // 1  QK^T done (and with it every earlier MMA of this CTA)
-    uint64_t* p_full = bars + 10;     // 1  P written to TMEM (S consumed)
-    uint64_t* o_full = bars + 11;     // 1  last PV done
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
-    const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int d = H * FA_D;
-    const int q0 = qb * FA_BQ;
-    const int n_tiles = causal ? min((Sk + FA_BK - 1) / FA_BK, qb + 1) : (Sk + FA_BK - 1) / FA_BK;
-    const int row_base = b * S;
-    const int kv_base = b * Sk;
-
-    if (threadIdx.x == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
-        fa_mbar_init(fa_smem_u32(q_full), 1);
-        for (int i = 0; i < 2; ++i) {
-            fa_mbar_init(fa_smem_u32(&k_full[i]), 1);
-            fa_mbar_init(fa_smem_u32(&k_empty[i]), 1);
-            fa_mbar_init(fa_smem_u32(&v_full[i]), 1);
-            fa_mbar_init(fa_smem_u32(&v_empty[i]), 1);
-        }
-        fa_mbar_init(fa_smem_u32(s_full), 1);
-        fa_mbar_init(fa_smem_u32(p_full), 4);          // one arrive per softmax warp
-        fa_mbar_init(fa_smem_u32(o_full), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fa_smem_u32(tmem_ptr)), "r"(FA_TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp < 4) {       // ones tile (bf16 1.0 = 0x3F80), generic-proxy writes made visible to the tensor core below
-        uint4* p1 = reinterpret_cast<uint4*>(sOne);
-        for (int i = threadIdx.x; i < FA_TILE_BYTES / 16; i += 128) p1[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    fa_fence_before();
-    __syncthreads();
-    fa_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S = tmem_base;            // columns [0,128): fp32 scores; P (bf16 pairs) is written over columns [0,64)
-    const uint32_t tmem_O = tmem_base + 128;      // columns [128,192): O accumulator
-    const uint32_t tmem_L = tmem_base + 192;      // columns [192,208): row sums (every column holds the same sum; column 0 is read)
-
-    if (warp == 4) {
-        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-        if (fa_elect()) {
-            fa_mbar_expect_tx(fa_smem_u32(q_full), FA_TILE_BYTES);
-            fa_tma_load_2d(&map_q, fa_smem_u32(q_full), fa_smem_u32(sQ), q_col0 + h * FA_D, row_base + q0);
-        }
-        __syncwarp();
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            fa_mbar_wait(fa_smem_u32(&k_empty[st]), ph ^ 1);
-            if (fa_elect()) {
-                fa_mbar_expect_tx(fa_smem_u32(&k_full[st]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_kv, fa_smem_u32(&k_full[st]), fa_smem_u32(sK + st * FA_TILE_BYTES), k_col0 + h * FA_D,
-                               kv_base + j * FA_BK);
-            }
-            __syncwarp();
-            fa_mbar_wait(fa_smem_u32(&v_empty[st]), ph ^ 1);
-            if (fa_elect()) {
-                fa_mbar_expect_tx(fa_smem_u32(&v_full[st]), FA_TILE_BYTES);
-                fa_tma_load_2d(&map_kv, fa_smem_u32(&v_full[st]), fa_smem_u32(sV + st * FA_TILE_BYTES), v_col0 + h * FA_D,
-                               kv_base + j * FA_BK);
-            }
-            __syncwarp();
-        }
-    } else if (warp == 5) {
-        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-        constexpr uint32_t idesc_qk = fa_idesc(128, 128, 0);
-        constexpr uint32_t idesc_pv = fa_idesc(128, 64, 1);
-        constexpr uint32_t idesc_l = fa_idesc(128, 16, 1);
-        const uint32_t q_addr = fa_smem_u32(sQ);
-        const uint32_t one_addr = fa_smem_u32(sOne);
-        auto issue_pv = [&](int j, bool last) {          // O += P(j) V(j); L += P(j) 1     (P in TMEM: 8 columns per 16 keys)
-            const int st = j & 1;
-            fa_mbar_wait(fa_smem_u32(p_full), j & 1);
-            fa_mbar_wait(fa_smem_u32(&v_full[st]), (j >> 1) & 1);
-            fa_fence_after();
-            const uint32_t v_addr = fa_smem_u32(sV + st * FA_TILE_BYTES);
-            if (fa_elect()) {
-#pragma unroll
-                for (int k = 0; k < FA_BK / 16; ++k) {
-                    fa_mma_ts(tmem_O, tmem_S + 8 * k, fa_desc(v_addr + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                    fa_mma_ts(tmem_L, tmem_S + 8 * k, fa_desc(one_addr + k * 2048), idesc_l, (j > 0 || k > 0) ? 1u : 0u);
-                }
-                fa_commit(fa_smem_u32(&v_empty[st]));
-                if (last) fa_commit(fa_smem_u32(o_full));
-            }
-            __syncwarp();
-        };
-        fa_mbar_wait(fa_smem_u32(q_full), 0);
-        for (int j = 0; j < n_tiles; ++j) {
-            const int st = j & 1;
-            const uint32_t ph = (j >> 1) & 1;
-            if (j > 0) issue_pv(j - 1, false);     // reads P(j-1) before Q K^T (j) overwrites the columns (in-order pipe)
-            fa_mbar_wait(fa_smem_u32(&k_full[st]), ph);
-            fa_fence_after();
-            if (fa_elect()) {
-                const uint64_t q_desc = fa_desc(q_addr);
-                const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA_TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < FA_D / 16; ++k) fa_mma(tmem_S, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                fa_commit(fa_smem_u32(&k_empty[st]));
-                fa_commit(fa_smem_u32(s_full));
-            }
-            __syncwarp();
-        }
-        issue_pv(n_tiles - 1, true);
-    } else {
-        // ===================== softmax warps 0..3: thread = query row =====================
-        const int r = warp * 32 + lane;                 // row inside the tile == TMEM lane
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        const float LOG2E = 1.4426950408889634f;
-        float m_ref = -INFINITY;                        // reference max of this row (raw score units)
-        for (int j = 0; j < n_tiles; ++j) {
-            fa_mbar_wait(fa_smem_u32(s_full), j & 1);
-            fa_fence_after();
-            const int valid = causal ? min(Sk - j * FA_BK, q0 + r - j * FA_BK + 1) : Sk - j * FA_BK;
-            const bool full_tile = (Sk - j * FA_BK >= FA_BK) && !(causal && j == qb);
-            // ---- pass A: row max of the tile (3-input max), the second half of the columns in flight during the first
-            float mx = -INFINITY;
-            {
-                uint32_t va[32], vb[32];
-                auto fold = [&](const uint32_t* v, int c) {
-                    if (full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
-                    }
-                };
-                fa_tmem_ld32(tmem_S + lane_off, va);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); fold(va, 0);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); fold(vb, 32);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); fold(va, 64);
-                fa_tmem_wait_ld(); fold(vb, 96);
-            }
-            // ---- reference max: moved only when the tile max exceeds it by more than 2^8 (then O and L are rescaled in TMEM;
-            // P V (j-1) has completed: s_full(j) was committed after it).  Rows without a valid key (cannot happen on the
-            // paths that use this kernel) keep their reference.
-            if (j == 0) {
-                m_ref = mx;
-            } else {
-                const bool grow = (mx - m_ref) * LOG2E > FA2_RESCALE_LOG2;
-                if (__any_sync(0xffffffffu, grow)) {
-                    const float f = grow ? fa_ex2((m_ref - mx) * LOG2E) : 1.0f;
-                    if (grow) m_ref = mx;
-#pragma unroll
-                    for (int c = 0; c < FA_D; c += 32) {
-                        uint32_t v[32];
-                        fa_tmem_ld32(tmem_O + lane_off + c, v);
-                        fa_tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-                        fa_tmem_st32(tmem_O + lane_off + c, v);
-                    }
-                    uint32_t lv;
-                    fa_tmem_ld1(tmem_L + lane_off, lv);
-                    fa_tmem_wait_ld();
-                    fa_tmem_st1(tmem_L + lane_off, __float_as_uint(__uint_as_float(lv) * f));
-                    fa_tmem_wait_st();
-                }
-            }
-            // ---- pass B: P = exp2((s - m_ref) log2e) -> bf16 pairs -> TMEM columns [c/2, c/2 + 16) of the score region
-            const float mneg = -m_ref * LOG2E;
-            {
-                uint32_t va[32], vb[32];
-                auto chunk = [&](const uint32_t* v, int c) {
-                    uint32_t pk[16];
-                    if (full_tile) {                       // warp-uniform: only the last key tile / the causal diagonal is masked
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 = fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg));
-                            const float p1 = fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg));
-                            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 = fa_mask0(fa_ex2(fmaf(__uint_as_float(v[i]), LOG2E, mneg)), c + i, valid);
-                            const float p1 = fa_mask0(fa_ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, mneg)), c + i + 1, valid);
-                            __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                        }
-                    }
-                    fa_tmem_st16(tmem_S + lane_off + (c >> 1), pk);
-                };
-                fa_tmem_ld32(tmem_S + lane_off, va);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 32, vb); chunk(va, 0);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 64, va); chunk(vb, 32);
-                fa_tmem_wait_ld(); fa_tmem_ld32(tmem_S + lane_off + 96, vb); chunk(va, 64);
-                fa_tmem_wait_ld(); chunk(vb, 96);
-            }
-            fa_tmem_wait_st();
-            fa_fence_before();
-            __syncwarp();
-            if (lane == 0) fa_mbar_arrive(fa_smem_u32(p_full));
-        }
-        // ---- epilogue: O / L
-        fa_mbar_wait(fa_smem_u32(o_full), 0);
-        fa_fence_after();
-        uint32_t lv;
-        fa_tmem_ld1(tmem_L + lane_off, lv);
-        fa_tmem_wait_ld();
-        const float inv = 1.0f / __uint_as_float(lv);
-        const int q = q0 + r;
-        __nv_bfloat16* orow = out + ((int64_t)(row_base + q)) * d + h * FA_D;
-#pragma unroll
-        for (int c = 0; c < FA_D; c += 32) {
-            uint32_t v[32];
-            fa_tmem_ld32(tmem_O + lane_off + c, v);
-            fa_tmem_wait_ld();
-            if (q < S) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-                    __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-                    __nv_bfloat162 h3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(orow + c + i) = pk;
-                }
-            }
-        }
-        fa_fence_before();
-    }
-    __syncthreads();
-    if (warp == 5) {
-        fa_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(FA_TMEM_COLS) : "memory");
-    }
-}
-
 // =====================================================================================================================
-// v3 (default): v2 with 64-key tiles and the score columns DOUBLE-BUFFERED in tensor memory, so that Q K^T of tile j+1
-// is already done when the softmax of tile j finishes: the softmax warps never wait for the tensor core in steady state
-// (in v2 they spent ~44 % of their time waiting for s_full, profiles/r02_encoder_attention_ncu.md).  With the warp-uniform
-// MMA issue a 64-key tile costs 12 back-to-back tcgen05.mma instead of 12 divergence loops, which is what made the smaller
-// tile a loss in round 1.  TMEM: S0 [0,64) | S1 [64,128) | O [128,192) | L [192,208) = 208 columns, 2 CTAs / SM.
+// The kernel.  Round 1 shipped a 128-key-tile kernel with P staged in shared memory and O folded into registers every tile
+// (444 TFLOP/s); its profile showed neither MUFU, tensor nor memory throughput saturated.  Round 2 found the cause in two
+// steps (profiles/r02_encoder_attention_ncu.md): (1) every tcgen05.mma was issued from `if (lane == 0)` code, which the
+// compiler wraps in a divergence loop (ELECT / BRA.U.ANY) — tens of cycles per MMA, so the 12-20 MMAs of a key tile took
+// longer to ISSUE than to execute and the softmax warps waited ~44 % of their time for S; (2) with warp-uniform issue the
+// softmax of tile j can be overlapped with Q K^T of tile j+1 by double-buffering 64-key score tiles in tensor memory.
+//   * P (bf16) is written back to TENSOR MEMORY over the score columns it was computed from (tcgen05.st) and P V runs with
+//     the A operand in TMEM: no shared-memory P tile, no swizzled 16-byte stores, no proxy fence;
+//   * O accumulates in TMEM across key tiles; the exponentials use a per-row REFERENCE max that only moves when the tile max
+//     exceeds it by more than 2^8 (then O and the row sum are rescaled in TMEM, warp-uniformly skipped otherwise) — exact,
+//     because numerator and denominator carry the same reference;
+//   * the row sum comes from the tensor core: a second MMA of P against a tile of ones accumulates sum_k P[r,k] into a TMEM
+//     column, from the same bf16-rounded P the numerator uses (no FADD per score); the row max uses the 3-input FMNMX;
+//   * the masked key tile (clip tail / causal diagonal) has its own code path (fa_mask0), the others run select-free.
+// TMEM: S0 [0,64) | S1 [64,128) | O [128,192) | L [192,208) = 208 columns, 2 CTAs / SM.
 //   MMA issue order:  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...     (P(j) overwrites the first 32 columns of S(j&1); QK(j+2)
 //   is issued after PV(j), and the tensor pipe executes in order).  O / L are rescaled (rarely) only after pv_done(j-1).
+// Measured (B200, 20 heads x 1500 keys, batch 8): 591 TFLOP/s; also tried and dropped: 128-key tiles without the double
+// buffer (518), eight softmax warps per CTA sharing rows through shared memory (555).
 constexpr int FA3_BK = 64;
 constexpr int FA3_KV_BYTES = FA3_BK * FA_D * 2;       // 8 KB
 constexpr int FA3_STAGES = 4;
 constexpr int FA3_SMEM = 1024 + FA_TILE_BYTES + FA3_KV_BYTES * (2 * FA3_STAGES + 1) + 512;    // Q, K x4, V x4, ones
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
-encoder_attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                              __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
     extern __shared__ unsigned char fa_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(fa_raw) + 1023) & ~(uintptr_t)1023);
@@ -1037,28 +480,17 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
             return TW_E_CUDA;
         }
         g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA2_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
     }
     if (causal && Sq != Sk) {
         ctx->set_error(TW_E_INVALID, "attention_tc: the causal mask needs as many queries as keys");
         return TW_E_INVALID;
     }
-    static const int variant = getenv("TWB200_FA_VARIANT") ? atoi(getenv("TWB200_FA_VARIANT")) : 3;
     CUtensorMap mq, mkv;
     TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
-    TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, variant == 3 ? FA3_BK : 128));
+    TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, FA3_BK));
     dim3 grid(ceil_div(Sq, FA_BQ), H, B);
-    if (variant == 3)
-        encoder_attention_tc3_kernel<<<grid, FA_THREADS, FA3_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
-    else if (variant == 2)
-        encoder_attention_tc2_kernel<<<grid, FA_THREADS, FA2_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
-    else if (variant == 0)
-        encoder_attention_tc_kernel<0><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
-    else
-        encoder_attention_tc_kernel<1><<<grid, FA_THREADS, FA_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
+    encoder_attention_tc_kernel<<<grid, FA_THREADS, FA3_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }
