@@ -28,4 +28,4 @@ for _ in range(4):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print(f"encoder large-v3 B=64 (TWB200_FA_VARIANT={os.environ.get('TWB200_FA_VARIANT', 'default')}): " + " ".join(f"{t:.1f}" for t in ts) + " ms")
+print(f"encoder large-v3 B=64 : " + " ".join(f"{t:.1f}" for t in ts) + " ms")
