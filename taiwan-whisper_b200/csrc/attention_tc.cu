@@ -227,6 +227,9 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     fa_fence_before();
     __syncthreads();
     fa_fence_after();
+    // programmatic dependent launch (encoder chain): barrier / TMEM / ones-tile setup above overlaps the previous kernel's tail
+    pdl_trigger();
+    pdl_wait();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_S = tmem_base;            // two score buffers of 64 columns; P (bf16 pairs) over the first 32 of each
     const uint32_t tmem_O = tmem_base + 128;
@@ -323,10 +326,16 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             fa_tmem_wait_ld();
             float mx = -INFINITY;
             if (full_tile) {
+                // four independent chains of 3-input max (a single chain is 32 dependent instructions per tile)
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) mx = fa_max3(mx, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+                for (int i = 0; i < 16; i += 2) {
+                    m0 = fa_max3(m0, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+                    m1 = fa_max3(m1, __uint_as_float(va[16 + i]), __uint_as_float(va[17 + i]));
+                    m2 = fa_max3(m2, __uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+                    m3 = fa_max3(m3, __uint_as_float(vb[16 + i]), __uint_as_float(vb[17 + i]));
+                }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < valid) ? __uint_as_float(va[i]) : -INFINITY);
@@ -490,7 +499,8 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
     TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
     TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, FA3_BK));
     dim3 grid(ceil_div(Sq, FA_BQ), H, B);
-    encoder_attention_tc_kernel<<<grid, FA_THREADS, FA3_SMEM, st>>>(mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0);
+    TW_CUDA_OK(ctx, launch_k(encoder_attention_tc_kernel, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0,
+                             causal ? 1 : 0));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }
