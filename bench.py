@@ -126,9 +126,9 @@ def sustained_tflops():
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_decode_attention_stream_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, bench shape)."""
+    (profiles/r02_decode_attention_stream_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, bench shape)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r01_decode_attention_stream_raw.csv")
+    p = os.path.join(ROOT, "profiles", "r02_decode_attention_stream_raw.csv")
     try:
         rows = list(csv.reader(open(p)))
         hdr, units, data = rows[0], rows[1], rows[2:]
@@ -600,7 +600,7 @@ def main():
             roof = {"kernel": "decode_attention_partial (cross-attention K/V streaming, 1 launch per layer per token)",
                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": which,
                     "traffic": ncu_traffic_bytes() if (args.model == MODEL and B == BATCH) else None,
-                    "traffic_source": "profiles/r01_decode_attention_stream.ncu-rep (ncu --set full, same shape)",
+                    "traffic_source": "profiles/r02_decode_attention_stream.ncu-rep (ncu --set full, same shape)",
                     "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
                     "algorithmic_bytes_per_launch": bytes_per_launch}
         # per-stage roofline of the last e2e step (north_star: every stage against HBM or tensor-core peak)

@@ -112,17 +112,19 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int ks = tile % ksplit, n_blk = tile / ksplit;
             const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
+            // grouped GEMM: this tile's output columns belong to group (n_blk*BN)/group_n, whose A slice starts K columns later per group
+            const int a_kb0 = epi.group_n > 0 ? ((n_blk * BN) / epi.group_n) * k_blocks_total : 0;
             for (int kb = kb0; kb < kb1; kb += SK2_KSUB) {
                 const uint32_t fb = smem_u32(&full_bar[stage]);
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 if (prefetched > 0) {
                     --prefetched;
-                    if (elect_one_sync()) tma_load_3d(&map_a, fb, sa, 0, 0, kb);
+                    if (elect_one_sync()) tma_load_3d(&map_a, fb, sa, 0, 0, a_kb0 + kb);
                 } else {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     if (elect_one_sync()) {
                         mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-                        tma_load_3d(&map_a, fb, sa, 0, 0, kb);
+                        tma_load_3d(&map_a, fb, sa, 0, 0, a_kb0 + kb);
                         tma_load_3d(&map_w, fb, sa + Cfg::A_REGION, 0, n_blk * BN, kb);
                     }
                 }
@@ -347,9 +349,18 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     // 64-wide tiles once 32-wide ones would need more than `waves` passes over the SMs (tuning knob TWB200_SK_WAVES; 1 = measured default: 2, i.e. fc1 as 160 32-wide
     // tiles on 148 CTAs instead of 80 64-wide ones, is 12 ms per decode slower)
     static const int waves = getenv("TWB200_SK_WAVES") ? atoi(getenv("TWB200_SK_WAVES")) : 1;
-    const int BN = (ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
+    int BN = (ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
+    int n_groups = 1;
+    if (epi.group_n > 0) {
+        if (epi.group_n % 32 || N % epi.group_n || epi.mode == EPI_RESID) {
+            ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc_skinny: grouped GEMM needs group_n % 32 == 0, N % group_n == 0 and a store epilogue");
+            return TW_E_UNSUPPORTED;
+        }
+        if (epi.group_n % BN) BN = 32;
+        n_groups = N / epi.group_n;
+    }
     CUtensorMap ma, mw;
-    TW_CHECK(sk2_map(ctx, A, M, K, lda, 64, &ma));
+    TW_CHECK(sk2_map(ctx, A, M, (int64_t)K * n_groups, lda, 64, &ma));
     TW_CHECK(sk2_map(ctx, W, N, K, ldw, BN, &mw));
     int tiles = ceil_div(N, BN);
     int ksplit = 1;

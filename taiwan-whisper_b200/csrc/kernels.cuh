@@ -39,6 +39,10 @@ struct GemmEpi {
     // kv_page_row(page_table, pt_stride, m, pos) of C2 (row pitch row2_stride) instead of m*ldc2 + pos*row2_stride
     const int32_t* page_table = nullptr;
     int pt_stride = 0;
+    // grouped GEMM (skinny kernel only): the output columns form groups of group_n, and group g multiplies its own K-wide slice of
+    // A — columns [g*K, (g+1)*K) of an A matrix that is n_groups*K wide — against rows [g*group_n, (g+1)*group_n) of W [N, K].
+    // Used by the absorbed cross-attention: q~_h = Wk_h^T q_h (group = head, K = 64) and o_h = Wv_h c_h (group = head, K = d).
+    int group_n = 0;
 };
 
 // CUDA-core FMA GEMM, fp32 accumulate in a fixed order; the fp32 check-mode path (T = float)
