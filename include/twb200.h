@@ -200,6 +200,18 @@ TW_API int tw_debug_set_row_budgets(tw_model* m, const int32_t* budgets_host, in
 TW_API int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype,
                   int epi_mode, const float* pos, int pos_period, int use_tc, void* stream);
 
+/* Test / profiling entry point: grouped form of the decode-step GEMM (bf16, M <= 64): the N output columns form groups of
+ * group_n; group g multiplies columns [g*K, (g+1)*K) of A [M, K*N/group_n] with rows [g*group_n, (g+1)*group_n) of W [N, K].
+ * The absorbed cross-attention uses it with group = head: q~_h = Wk_h^T q_h (K = 64) and o_h = Wv_h c_h + bv_h (K = d). */
+TW_API int tw_debug_gemm_grouped(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int group_n,
+                                 void* stream);
+/* Test / profiling entry point: absorbed decoder cross-attention (bf16).  qt: [B*H + 24 rows, 64*H], row clip*H + h = q~ of that
+ * clip and head (the 24 trailing rows only need to be readable); enc: [B*Tk, 64*H] encoder output; out: [B, H*64*H], row clip,
+ * columns [h*d, (h+1)*d) = softmax_k(q~_h . enc[clip, k]) . enc[clip]  (HF modeling_whisper.py:284-358 with K and V projected after
+ * the contraction).  active / n_active (device, nullable): compacted list of the clips to process; rev != 0 walks the keys backwards. */
+TW_API int tw_debug_absorbed_attention(tw_ctx* ctx, const void* qt, const void* enc, int Tk, int B, int H, void* out, const int32_t* active,
+                                       const int32_t* n_active, int rev, void* stream);
+
 /* Test / profiling entry points for the two attention kernels of the path (device buffers):
  *   decode attention: q [B, q_stride] (first H*64 elements used), K|V rows kv [B][Tk][2*H*64] with clip
  *   stride kv_clip_stride elements -> out [B, H*64]   (softmax(q.K^T).V per head, q pre-scaled)

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtwb200.so")
-SOURCES = ["logmel.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_skinny.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "select.cu", "model.cu"]
+SOURCES = ["logmel.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_skinny.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "absorb.cu", "select.cu", "model.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

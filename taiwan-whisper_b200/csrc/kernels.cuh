@@ -127,6 +127,17 @@ void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv
                            T* out, cudaStream_t st, const int32_t* page_table = nullptr, int pt_stride = 0,
                            const int32_t* finished = nullptr);
 
+// ---- absorbed cross-attention (absorb.cu), bf16 only: scores and values straight from the encoder output through per-head
+// q~ = Wk_h^T q_h; returns c_h = softmax(q~_h . E^T) E per clip and head.  qt [B*H + ABSORB_QT_PAD rows, d] (row clip*H + h),
+// enc [B*Tk, d], partial f32 [absorbed_attention_partial_floats], ctx_out [B, H*d]; rev walks the key tiles backwards.
+constexpr int ABSORB_QT_PAD = 24;
+int absorbed_attention_init(tw_ctx* ctx);
+bool absorbed_attention_supported(int H, int d);
+size_t absorbed_attention_partial_floats(int B, int H, int d);
+int absorbed_attention(tw_ctx* ctx, const __nv_bfloat16* qt, const __nv_bfloat16* enc, int Tk, int B, int H, int d, float* partial,
+                       __nv_bfloat16* ctx_out, cudaStream_t st, const int32_t* active = nullptr, const int32_t* n_active = nullptr,
+                       int rev = 0, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+
 // ---- token selection (select.cu)
 struct RulesDev {
     const uint8_t* suppress_mask;        // [V] 1 = always suppressed

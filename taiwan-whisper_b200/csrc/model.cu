@@ -67,6 +67,7 @@ struct AttnW {
     float* q_b = nullptr;
     void* kv_w = nullptr;    // cross-attn: [2d, d] = [Wk; Wv]
     float* kv_b = nullptr;   // [2d] = [0; bv]
+    void* kt_w = nullptr;    // cross-attn, absorbed path (bf16): [H*d, 64], row h*d + c = Wk[h*64 .. h*64+63, c] (per-head Wk^T)
     void* o_w = nullptr;     // [d, d]
     float* o_b = nullptr;
 };
@@ -83,9 +84,10 @@ struct LayerW {
 
 struct GraphKey {
     int B, eos, pad, ts_begin, no_ts, max_init, budget;
+    const void* enc;       // the absorbed cross-attention reads the encoder output directly: the graph bakes the pointer in
     bool operator<(const GraphKey& o) const {
-        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, budget) <
-               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.budget);
+        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, budget, enc) <
+               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.budget, o.enc);
     }
 };
 struct GraphEntry {
@@ -125,6 +127,12 @@ struct tw_model {
     float *dx = nullptr, *dlogits = nullptr, *dpartial = nullptr;
     int64_t ld_logits = 0;     // row pitch of dlogits: vocab rounded up to 4 floats (16-byte rows for the TMA-store epilogue)
     void *dxn = nullptr, *dqkv = nullptr, *datt = nullptr, *dq = nullptr, *dhmid = nullptr;
+    // absorbed cross-attention (bf16 product path, decode batches <= 64): q~ [maxB*H + pad, d], c [maxB, H*d], partial records
+    bool absorb_ok = false;      // the model has the weights / buffers of the absorbed path
+    bool absorb_now = false;     // the decode call in progress uses it
+    const void* cur_enc = nullptr;   // encoder output of the decode call in progress
+    void *dqt = nullptr, *dctx = nullptr;
+    float* dab_partial = nullptr;
     int32_t* dstate = nullptr;  // decode state: 8 arrays of maxB ints + counters (DecodeState)
     int32_t* d_row_budget = nullptr;   // [maxB] per-row token budgets (tw_debug_set_row_budgets)
     bool row_budget_on = false;
@@ -186,6 +194,18 @@ struct WeightTable {
     }
 };
 
+// kt[h*d + c][j] = w[h*64 + j][c]: per-head transpose of a [d, d] projection (absorbed cross-attention, q~_h = Wk_h^T q_h)
+template <typename T>
+__global__ void head_transpose_kernel(const T* __restrict__ w, T* __restrict__ kt, int H, int d) {
+    const int64_t n = (int64_t)d * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % 64);
+        const int64_t hc = i / 64;
+        const int c = (int)(hc % d), h = (int)(hc / d);
+        kt[i] = w[(int64_t)(h * 64 + j) * d + c];
+    }
+}
+
 template <typename T>
 int put(tw_model* m, const WeightTable& wt, const std::string& name, int64_t numel, T* dst, float scale = 1.0f) {
     const tw_weight* w = wt.get(m->ctx, name, numel);
@@ -220,6 +240,10 @@ int load_attn(tw_model* m, const WeightTable& wt, const std::string& pre, AttnW&
         TW_CHECK(put<T>(m, wt, pre + "k_proj.weight", dd, (T*)a.kv_w));
         TW_CHECK(put<T>(m, wt, pre + "v_proj.weight", dd, (T*)a.kv_w + dd));
         TW_CHECK(put<float>(m, wt, pre + "v_proj.bias", d, a.kv_b + d));
+        if (m->absorb_ok) {
+            TW_CHECK(dev_alloc(m, &a.kt_w, dd * sizeof(T)));
+            head_transpose_kernel<T><<<nblocks(dd), 256>>>((const T*)a.kv_w, (T*)a.kt_w, m->desc.heads, d);
+        }
     }
     TW_CHECK(dev_alloc(m, &a.o_w, dd * sizeof(T)));
     TW_CHECK(dev_alloc(m, (void**)&a.o_b, d * sizeof(float)));
@@ -330,6 +354,14 @@ int alloc_workspace(tw_model* m) {
     TW_CHECK(dev_alloc(m, &m->datt, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dq, B * d * e));
     TW_CHECK(dev_alloc(m, &m->dhmid, B * D.ffn * e));
+    if (m->absorb_ok) {
+        const size_t Bd = B < 64 ? B : 64;          // the absorbed path serves decode batches of up to 64 clips (skinny GEMMs)
+        TW_CHECK(dev_alloc(m, &m->dqt, (Bd * D.heads + ABSORB_QT_PAD) * d * e));
+        TW_CUDA_OK(m->ctx, cudaMemset(m->dqt, 0, (Bd * D.heads + ABSORB_QT_PAD) * d * e));
+        TW_CHECK(dev_alloc(m, &m->dctx, Bd * D.heads * d * e));
+        TW_CUDA_OK(m->ctx, cudaMemset(m->dctx, 0, Bd * D.heads * d * e));
+        TW_CHECK(dev_alloc(m, (void**)&m->dab_partial, absorbed_attention_partial_floats((int)Bd, D.heads, (int)d) * sizeof(float)));
+    }
     m->ld_logits = ((int64_t)D.vocab + 3) / 4 * 4;
     TW_CHECK(dev_alloc(m, (void**)&m->dlogits, B * (size_t)m->ld_logits * sizeof(float)));
     const size_t partial_floats = decode_attention_partial_floats((int)B, D.heads);
@@ -541,6 +573,34 @@ struct StepIo {
     float* logits_tap;
 };
 
+// Absorbed cross-attention of one decoder layer (absorb.cu): q [B, d] -> att [B, d] (the input of the output projection).
+//   q~ = per-head Wk^T q (grouped GEMM, K = 64), c = softmax(q~ . E^T) E streamed from the encoder output, o = per-head Wv c + bv
+template <typename T>
+int cross_absorbed(tw_model* m, const LayerW& L, const T* q, T* att, int B, int layer, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1,
+                   const DecodeState& S);
+template <>
+int cross_absorbed<float>(tw_model* m, const LayerW&, const float*, float*, int, int, cudaStream_t, cudaEvent_t, cudaEvent_t, const DecodeState&) {
+    m->ctx->set_error(TW_E_UNSUPPORTED, "absorbed cross-attention is a bf16 path");
+    return TW_E_UNSUPPORTED;
+}
+template <>
+int cross_absorbed<__nv_bfloat16>(tw_model* m, const LayerW& L, const __nv_bfloat16* q, __nv_bfloat16* att, int B, int layer, cudaStream_t st,
+                                  cudaEvent_t e0, cudaEvent_t e1, const DecodeState& S) {
+    typedef __nv_bfloat16 T;
+    const int d = m->desc.d_model, H = m->desc.heads;
+    const char* er = getenv("TWB200_AB_REV");
+    const bool serpentine = !(er && strcmp(er, "0") == 0);
+    GemmEpi qe = mk_epi(EPI_STORE, nullptr, m->dqt, (int64_t)H * d);
+    qe.group_n = d;
+    TW_CHECK(gemm<T>(m, q, d, (const T*)L.cross.kt_w, 64, B, H * d, 64, qe, st));
+    TW_CHECK(absorbed_attention(m->ctx, (const T*)m->dqt, (const T*)m->cur_enc, TW_N_CTX, B, H, d, m->dab_partial, (T*)m->dctx, st, S.active,
+                                S.n_active, serpentine ? (layer & 1) : 0, e0, e1));
+    GemmEpi ve = mk_epi(EPI_STORE, L.cross.kv_b + d, att, d);
+    ve.group_n = 64;
+    TW_CHECK(gemm<T>(m, (const T*)m->dctx, (int64_t)H * d, (const T*)L.cross.kv_w + (size_t)d * d, d, B, d, d, ve, st));
+    return TW_OK;
+}
+
 // One decode step (all kernels of one token position).  Position, prompt and output stride are read from
 // m->d_step on the device, so the same launch sequence — or one captured CUDA graph — serves every position.
 template <typename T>
@@ -608,10 +668,14 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
             e0 = m->prof_ev[m->prof_used];
             e1 = m->prof_ev[m->prof_used + 1];
             m->prof_used += 2;
-            m->prof_bytes = (double)B * TW_N_CTX * 2 * d * sizeof(T);
+            m->prof_bytes = (double)B * TW_N_CTX * (m->absorb_now ? 1 : 2) * d * sizeof(T);
         }
-        decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial, att,
-                            st, e0, e1, S.active, S.n_active);
+        if (m->absorb_now) {
+            TW_CHECK(cross_absorbed<T>(m, L, q, att, B, l, st, e0, e1, S));
+        } else {
+            decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial, att,
+                                st, e0, e1, S.active, S.n_active);
+        }
         mark(l, "cross_attn+combine");
         TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
         mark(l, "cross_o");
@@ -679,7 +743,8 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     StepIo io{out_tokens, out_lengths, forced, logits_tap};
     if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
     if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
-    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, m->row_budget_on ? 1 : 0};
+    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, m->row_budget_on ? 1 : 0,
+                 m->absorb_now ? m->cur_enc : nullptr};
     cudaGraphExec_t exec = nullptr;
     uint64_t exec_kernels = 0;
 
@@ -769,6 +834,22 @@ bool check_model(tw_model* m, const char* fn) {
     return m && m->ctx && fn;
 }
 
+// The absorbed cross-attention (absorb.cu) serves the bf16 tensor-core path at decode batches the skinny GEMMs take (<= 64 clips);
+// TWB200_ABSORB=0 keeps the per-layer K|V store (A/B knob).  Larger batches and the fp32 check mode stream the K|V store.
+bool use_absorb(const tw_model* m, int B) {
+    const char* e = getenv("TWB200_ABSORB");       // read per call: tests switch it between decode calls
+    const bool env_on = !(e && strcmp(e, "0") == 0);
+    return env_on && m->absorb_ok && m->use_tc && m->use_tc_skinny && B <= 64;
+}
+
+// cross-attention K|V of every decoder layer (once per window) — not needed when the decode reads the encoder output directly
+int cross_kv_for_decode(tw_model* m, const void* enc_out, int B, cudaStream_t st) {
+    m->cur_enc = enc_out;
+    m->absorb_now = use_absorb(m, B);
+    if (m->absorb_now) return TW_OK;
+    return m->desc.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, enc_out, B, st) : cross_kv_impl<float>(m, enc_out, B, st);
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -803,6 +884,7 @@ int tw_ctx_create(int device, tw_ctx** out) {
     TW_CHECK(logmel_init(ctx));
     TW_CHECK(gemm_tc_init(ctx));
     TW_CHECK(gemm_tc_skinny_init(ctx));
+    TW_CHECK(absorbed_attention_init(ctx));
     return TW_OK;
 }
 
@@ -852,6 +934,7 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_pdl = !(gp && strcmp(gp, "0") == 0);
     const char* gtr = getenv("TWB200_TRACE");
     m->trace_pos = gtr ? atoi(gtr) : -1;
+    m->absorb_ok = (D.dtype == TW_BF16) && absorbed_attention_supported(D.heads, D.d_model);
     WeightTable wt;
     for (size_t i = 0; i < n; ++i)
         if (table[i].name) wt.by_name[table[i].name] = &table[i];
@@ -900,7 +983,8 @@ size_t tw_workspace_bytes(const tw_model_desc* desc) {
     auto al = [](size_t b) { return b == 0 ? (size_t)16 : b; };      // dev_alloc never asks for 0 bytes
     const size_t ln = 2 * al(d * f4);
     const size_t attn_self = al(3 * dd * e) + al(3 * d * f4) + al(dd * e) + al(d * f4);
-    const size_t attn_cross = al(dd * e) + al(d * f4) + al(2 * dd * e) + al(2 * d * f4) + al(dd * e) + al(d * f4);
+    const bool absorb = D.dtype == TW_BF16 && absorbed_attention_supported(D.heads, D.d_model);
+    const size_t attn_cross = al(dd * e) + al(d * f4) + al(2 * dd * e) + al(2 * d * f4) + al(dd * e) + al(d * f4) + (absorb ? al(dd * e) : 0);
     const size_t mlp = al(ffn * d * e) + al(ffn * f4) + al(ffn * d * e) + al(d * f4);
     size_t w = al(d * 3 * D.n_mel * e) + al(d * 3 * d * e) + 2 * al(d * f4) + al((size_t)TW_N_CTX * d * f4);
     w += (size_t)D.enc_layers * (ln + attn_self + ln + mlp) + ln;
@@ -914,6 +998,11 @@ size_t tw_workspace_bytes(const tw_model_desc* desc) {
                 al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * ((V + 3) / 4 * 4) * f4) +
                 al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((8 * B + 8) * sizeof(int32_t)) + al(V) + al(V) +
                 al(4096 * sizeof(int32_t)) + al(B * D.max_target * sizeof(int32_t)) + al(B * sizeof(int32_t)) + al(STEP_INTS * sizeof(int32_t));
+    if (absorb) {
+        const size_t Bd = B < 64 ? B : 64;
+        ws += al((Bd * D.heads + ABSORB_QT_PAD) * d * e) + al(Bd * D.heads * d * e) +
+              al(absorbed_attention_partial_floats((int)Bd, D.heads, (int)d) * f4);
+    }
     return w + ws;
 }
 
@@ -961,7 +1050,7 @@ int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* pro
     RulesDev R;
     TW_CHECK(upload_rules(m, rules, &R, st));
     cudaEventRecord(m->ev[2], st);
-    int r = m->desc.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, enc_out, B, st) : cross_kv_impl<float>(m, enc_out, B, st);
+    int r = cross_kv_for_decode(m, enc_out, B, st);
     if (r != TW_OK) return r;
     cudaEventRecord(m->ev[3], st);
     r = m->desc.dtype == TW_BF16
@@ -1027,7 +1116,7 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
                                : encode_impl<float>(m, m->ws_mel, B, m->ws_enc, -1, nullptr, st, clip_max);
     if (r != TW_OK) return r;
     cudaEventRecord(m->ev[2], st);
-    r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, m->ws_enc, B, st) : cross_kv_impl<float>(m, m->ws_enc, B, st);
+    r = cross_kv_for_decode(m, m->ws_enc, B, st);
     if (r != TW_OK) return r;
     cudaEventRecord(m->ev[3], st);
     r = D.dtype == TW_BF16
@@ -1041,6 +1130,31 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
     for (int i = 0; i < 5; ++i) m->ev_valid[i] = true;
     m->ev_valid[6] = true;
     return TW_OK;
+}
+
+int tw_debug_gemm_grouped(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int group_n,
+                          void* stream) {
+    if (!ctx || !A || !W || !C || group_n <= 0 || N % group_n) return TW_E_INVALID;
+    GemmEpi e = mk_epi(EPI_STORE, bias, C, N);
+    e.group_n = group_n;
+    ctx->launches += 1;
+    return gemm_tc_skinny(ctx, (const __nv_bfloat16*)A, (int64_t)K * (N / group_n), (const __nv_bfloat16*)W, K, M, N, K, e, (cudaStream_t)stream);
+}
+
+int tw_debug_absorbed_attention(tw_ctx* ctx, const void* qt, const void* enc, int Tk, int B, int H, void* out, const int32_t* active,
+                                const int32_t* n_active, int rev, void* stream) {
+    if (!ctx || !qt || !enc || !out || B <= 0 || H <= 0 || Tk <= 0) return TW_E_INVALID;
+    const int d = 64 * H;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = nullptr;
+    TW_CUDA_OK(ctx, cudaMalloc(&partial, absorbed_attention_partial_floats(B, H, d) * sizeof(float)));
+    ctx->launches += 2;
+    const int r = absorbed_attention(ctx, (const __nv_bfloat16*)qt, (const __nv_bfloat16*)enc, Tk, B, H, d, partial, (__nv_bfloat16*)out, st,
+                                     active, n_active, rev);
+    cudaStreamSynchronize(st);
+    cudaFree(partial);
+    if (r == TW_OK) TW_CUDA_OK(ctx, cudaGetLastError());
+    return r;
 }
 
 int tw_debug_gemm(tw_ctx* ctx, const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int dtype, int epi_mode,

@@ -227,6 +227,85 @@ def test_general_attention_kernels_vs_torch(B, Sq, Sk, H, causal, impl, dtype):
     assert err < (2e-5 if dtype == "f32" else 2e-2), err
 
 
+@pytest.mark.parametrize("M,H,K,group_n", [(64, 20, 64, 1280), (64, 20, 1280, 64), (3, 6, 64, 384), (5, 6, 384, 64), (64, 2, 128, 64),
+                                            (64, 16, 64, 1024)])
+def test_gemm_grouped_vs_torch(M, H, K, group_n):
+    """Grouped form of the skinny GEMM (absorbed cross-attention: q~_h = Wk_h^T q_h with K = 64, o_h = Wv_h c_h + bv_h with K = d)."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    N = H * group_n
+    g = torch.Generator(device="cuda").manual_seed(M + H + K + group_n)
+    A = (torch.randn((M, H * K), device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn((N, K), device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn((N,), device="cuda", generator=g) * 0.1
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    ctx.check(ctx.lib.tw_debug_gemm_grouped(ctx.handle, A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, group_n,
+                                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = torch.einsum("mhk,hnk->mhn", A.float().view(M, H, K), W.float().view(H, group_n, K)).reshape(M, N) + bias
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+
+
+def _absorbed_ref(qt, enc, B, Tk, H):
+    d = 64 * H
+    E = enc.float().view(-1, Tk, d)[:B]
+    q = qt.float()[:B * H].view(B, H, d)
+    sc = torch.einsum("bhd,btd->bht", q, E)
+    return torch.einsum("bht,btd->bhd", torch.softmax(sc, -1), E).reshape(B, H * d)
+
+
+@pytest.mark.parametrize("Tk,B,H", [(1500, 64, 20), (1500, 3, 6), (1500, 32, 16), (200, 5, 2), (64, 1, 12), (1, 2, 8), (129, 7, 20)])
+@pytest.mark.parametrize("rev", [0, 1])
+def test_absorbed_attention_kernel_vs_torch(Tk, B, H, rev):
+    """Absorbed cross-attention (absorb.cu): c[b, h] = softmax_k(q~[b, h] . E[b, k]) E[b] against torch fp32 on the same bf16 inputs;
+    score magnitudes chosen so that the lazy reference maximum moves several times per clip."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(Tk * 3 + B * 5 + H)
+    enc = torch.randn((B * Tk, d), device="cuda", generator=g).bfloat16()
+    qt = torch.zeros((B * H + 24, d), device="cuda", dtype=torch.bfloat16)
+    # per-(clip, head) scale: some heads nearly uniform, some peaked (scores up to ~ +-40)
+    scale = torch.rand((B * H, 1), device="cuda", generator=g) * 8.0 / d ** 0.5
+    qt[:B * H] = (torch.randn((B * H, d), device="cuda", generator=g) * scale).bfloat16()
+    out = torch.zeros((B, H * d), device="cuda", dtype=torch.bfloat16)
+    ctx.check(ctx.lib.tw_debug_absorbed_attention(ctx.handle, qt.data_ptr(), enc.data_ptr(), Tk, B, H, out.data_ptr(), None, None, rev,
+                                                  torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _absorbed_ref(qt, enc, B, Tk, H)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), (err, ref.abs().max().item())
+
+
+def test_absorbed_attention_active_list():
+    """Only the clips of the compacted active list are streamed; their results equal the full run, the others are untouched."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    Tk, B, H = 1500, 9, 6
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(77)
+    enc = torch.randn((B * Tk, d), device="cuda", generator=g).bfloat16()
+    qt = torch.zeros((B * H + 24, d), device="cuda", dtype=torch.bfloat16)
+    qt[:B * H] = (torch.randn((B * H, d), device="cuda", generator=g) * 3.0 / d ** 0.5).bfloat16()
+    act = [0, 3, 4, 8]
+    active = torch.tensor(act + [0] * (B - len(act)), device="cuda", dtype=torch.int32)
+    n_active = torch.tensor([len(act)], device="cuda", dtype=torch.int32)
+    out = torch.full((B, H * d), 7.0, device="cuda", dtype=torch.bfloat16)
+    ctx.check(ctx.lib.tw_debug_absorbed_attention(ctx.handle, qt.data_ptr(), enc.data_ptr(), Tk, B, H, out.data_ptr(), active.data_ptr(),
+                                                  n_active.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _absorbed_ref(qt, enc, B, Tk, H)
+    for b in range(B):
+        if b in act:
+            assert (out[b].float() - ref[b]).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item()), b
+        else:
+            assert (out[b].float() == 7.0).all(), b
+
+
 @pytest.mark.parametrize("Tk,B,H", [(1500, 3, 6), (1, 2, 2), (37, 5, 20), (448, 64, 2)])
 @pytest.mark.parametrize("entry", ["tw_debug_decode_attention", "tw_debug_self_attention"])
 def test_decode_attention_kernel_vs_torch(Tk, B, H, entry):
