@@ -118,7 +118,9 @@ template <int TK>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_qt, int Tk, int B, int H,
                           int d, int NS, float* __restrict__ partial, const int32_t* __restrict__ active,
-                          const int32_t* __restrict__ n_active, int rev, int desc_swap) {
+                          const int32_t* __restrict__ n_active, int rev, int desc_swap, long long* __restrict__ trace) {
+    // bring-up timeline (TWB200_AB_TRACE): clock64 of CTA 0's pipeline events, 64 slots per tile
+#define AB_TRACE(tile, slot) do { if (trace && blockIdx.x == 0 && (tile) < 16 && lane == 0) trace[(tile) * 64 + (slot)] = clock64(); } while (0)
     constexpr int BOX = TK * 128;             // one TMA box: TK keys x 64 features
     constexpr int SLICE = 2 * BOX;            // one ring slot: 128 features of a tile
     extern __shared__ unsigned char ab_raw[];
@@ -183,6 +185,7 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
         auto load_slice = [&](int row, int p) {
             const int slot = c % NS;
             mbar_wait(smem_u32(&st_empty[slot]), ((c / NS) & 1) ^ 1);
+            AB_TRACE((int)(c / npair), (int)(c % npair));
             if (elect_one_sync()) {
                 const uint32_t fb = smem_u32(&st_full[slot]);
                 const uint32_t dst = smem_u32(sRing + (size_t)slot * SLICE);
@@ -240,6 +243,7 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
                 const int ring = c1 % NS;
                 mbar_wait(smem_u32(&st_full[ring]), (c1 / NS) & 1);
                 tc_fence_after();
+                AB_TRACE(g + p1_tile, 10 + p1_slice);
                 const uint32_t d_tmem = tmem_S + ((g + p1_tile) & 1) * AB_NP;
                 if (elect_one_sync()) {
                     const uint32_t sa = smem_u32(sRing + (size_t)ring * SLICE);
@@ -262,8 +266,10 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
                 // look ahead into tile t + 1 as far as the ring allows without waiting for slots that pass 2 of tile t releases
                 while (p1_tile == t + 1 && p1_tile < nt && c1 < c2 + (uint32_t)NS) pass1_slice();
                 // pass 2: C^T(tile p) += E_slice^T . P^T
+                AB_TRACE(g + t, 20);
                 mbar_wait(smem_u32(p_full), (g + t) & 1);
                 tc_fence_after();
+                AB_TRACE(g + t, 21);
                 for (int p = 0; p < npair; ++p) {
                     const int ring = c2 % NS;
                     mbar_wait(smem_u32(&st_full[ring]), (c2 / NS) & 1);
@@ -284,6 +290,7 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
                     __syncwarp();
                     ++c2;
                 }
+                AB_TRACE(g + t, 22);
             }
             g += nt;
         }
@@ -304,11 +311,14 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
             for (int t = 0; t < nt; ++t, ++g) {
                 const int tt = rev ? nt - 1 - t : t;
                 const bool valid = lane < 16 && kk < TK && tt * TK + kk < nkeys;     // this lane holds a key of the segment
+                if (warp == 0) AB_TRACE(g, 29);
                 mbar_wait(smem_u32(&s_full[g & 1]), (g >> 1) & 1);
                 tc_fence_after();
+                if (warp == 0) AB_TRACE(g, 30);
                 uint32_t sv[32];
                 tmem_ld32(tmem_S + lane_off + (g & 1) * AB_NP, sv);
                 tmem_ld_wait();
+                if (warp == 0) AB_TRACE(g, 31);
                 bool slow = (t == 0);
                 if (t > 0) {
                     bool grow = false;
@@ -318,10 +328,12 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
                     slow = ab_bar_or(grow);
                 }
                 // P^T (single buffer) is read and C^T accumulated by pass 2 of the previous tile
+                if (warp == 0) AB_TRACE(g, 32);
                 if (g > 0) {
                     mbar_wait(smem_u32(pv_done), (g - 1) & 1);
                     tc_fence_after();
                 }
+                if (warp == 0) AB_TRACE(g, 33);
                 if (slow) {
                     // exact per-head maximum of the tile: 16 lanes by shuffles, the four warps through shared memory
                     float mx[AB_NQ];
@@ -378,6 +390,7 @@ absorbed_attention_kernel(const __grid_constant__ CUtensorMap map_e, const __gri
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(p_full));
+                if (warp == 0) AB_TRACE(g, 34);
             }
             // ---- end of the clip segment: partial record (m, l, C) of this (CTA, clip)
             mbar_wait(smem_u32(pv_done), (g - 1) & 1);
@@ -489,7 +502,7 @@ static int ab_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t cols, int 
 
 static int ab_tile_keys() {
     static const int tk = getenv("TWB200_AB_TK") ? atoi(getenv("TWB200_AB_TK")) : 64;
-    return tk == 48 ? 48 : 64;
+    return (tk == 48 || tk == 32) ? tk : 64;
 }
 // ring slots that fit next to Q~ (at least one whole tile)
 static int ab_ring_slots(int d, int tk) {
@@ -520,6 +533,7 @@ int absorbed_attention_init(tw_ctx* ctx) {
     }
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(absorbed_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_MAX));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(absorbed_attention_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_MAX));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(absorbed_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_MAX));
     return TW_OK;
 }
 
@@ -528,7 +542,7 @@ int absorbed_attention_init(tw_ctx* ctx) {
 static_assert(ABSORB_QT_PAD == AB_NQ, "the Q~ matrix is padded by one TMA box of rows");
 int absorbed_attention(tw_ctx* ctx, const __nv_bfloat16* qt, const __nv_bfloat16* enc, int Tk, int B, int H, int d, float* partial,
                        __nv_bfloat16* ctx_out, cudaStream_t st, const int32_t* active, const int32_t* n_active, int rev, cudaEvent_t ev0,
-                       cudaEvent_t ev1) {
+                       cudaEvent_t ev1, long long* trace) {
     if (!absorbed_attention_supported(H, d) || !g_ab_encode) {
         ctx->set_error(TW_E_UNSUPPORTED, "absorbed_attention: needs H <= 24, d a multiple of 128 up to 1280 and absorbed_attention_init");
         return TW_E_UNSUPPORTED;
@@ -543,10 +557,13 @@ int absorbed_attention(tw_ctx* ctx, const __nv_bfloat16* qt, const __nv_bfloat16
     if (ev0) cudaEventRecord(ev0, st);
     if (tk == 64)
         TW_CUDA_OK(ctx, launch_k(absorbed_attention_kernel<64>, dim3(G), dim3(AB_THREADS), ab_smem_bytes(d, tk, ns), st, me, mq, Tk, B, H, d, ns,
-                                 partial, active, n_active, rev, desc_swap));
+                                 partial, active, n_active, rev, desc_swap, trace));
+    else if (tk == 32)
+        TW_CUDA_OK(ctx, launch_k(absorbed_attention_kernel<32>, dim3(G), dim3(AB_THREADS), ab_smem_bytes(d, tk, ns), st, me, mq, Tk, B, H, d, ns,
+                                 partial, active, n_active, rev, desc_swap, trace));
     else
         TW_CUDA_OK(ctx, launch_k(absorbed_attention_kernel<48>, dim3(G), dim3(AB_THREADS), ab_smem_bytes(d, tk, ns), st, me, mq, Tk, B, H, d, ns,
-                                 partial, active, n_active, rev, desc_swap));
+                                 partial, active, n_active, rev, desc_swap, trace));
     if (ev1) cudaEventRecord(ev1, st);
     TW_CUDA_OK(ctx, launch_k(absorbed_attention_combine<__nv_bfloat16>, dim3(H, B), dim3(256), 0, st, (const float*)partial, Tk, B, G, tk, H, d,
                              ctx_out, active, n_active));

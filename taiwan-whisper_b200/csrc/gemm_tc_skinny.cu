@@ -5,9 +5,12 @@
 // stages were in flight (tools/probes/gemm_trace.py) — the number of outstanding TMA operations, not bytes, is
 // what saturates.  This variant makes each operation 4x larger: the operands are described by 3-D tensor maps
 // (64 K-elements x rows x K-blocks) and one box fetches KSUB = 4 consecutive K blocks, landing as KSUB
-// 128-byte-swizzled K-major tiles.  A is fetched as a 64-row box (8 KB per K block); the MMA still runs as
-// M = 128 and reads 8 KB past the A tile as rows 64..127 — those accumulator rows are never stored and rows do
-// not mix inside an MMA.
+// 128-byte-swizzled K-major tiles.  A is fetched as a 64-row box (8 KB per K block) and the MMA runs as M = 64:
+// a tcgen05.mma of this size is paced by its A operand at ~one row per cycle whatever N is (measured: ~100-130
+// cycles per M128 N32 K16 instruction here and in absorb.cu, ~63 per M64 N24 K16; profiles/r02_mma_small_n.md), so
+// the M = 128 form of round 1 — which read 64 rows past the tile as accumulator rows nobody stored — paid twice
+// for the K loop, and N up to 128 rides free.  Accumulator row r of an M = 64 instruction sits in TMEM lane
+// (r % 16) + 32 (r / 16): every epilogue warp owns 16 rows in its lanes 0-15.
 // Same roles as gemm_tc.cu: warp 0 TMA producer (weights prefetched before griddepcontrol.wait), warp 1 MMA
 // issuer + TMEM owner, warps 2-5 epilogue (bias / GELU / fp32 residual add with split-K atomics / fp32 store /
 // KV-cache scatter of the fused QKV projection).
@@ -29,13 +32,11 @@ template <int BN, int AROWS> struct Sk2Cfg {
     static constexpr int W_SUB = BN * 64 * 2;
     static constexpr int A_REGION = SK2_KSUB * A_SUB;
     static constexpr int STAGE_BYTES = SK2_KSUB * (A_SUB + W_SUB);         // 48 KB (BN 32) / 64 KB (BN 64)
-    static constexpr int STAGES = (BN == 32) ? 4 : 3;
+    static constexpr int STAGES = (BN == 32) ? 4 : (BN == 64 ? 3 : 2);
     static constexpr int MIN_CTAS = 1;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-    // the MMA runs as M = 128 and reads 128 x 128 B from the start of every A tile: the read of the last tile must stay
-    // inside the stage (rows >= AROWS are never stored)
-    static_assert((SK2_KSUB - 1) * A_SUB + 128 * 128 <= STAGE_BYTES, "the M=128 read of the last A tile must stay inside the stage");
+    static_assert(AROWS == 64, "the MMA runs as M = 64 over the whole A box");
 };
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -134,7 +135,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
-        constexpr uint32_t idesc = make_idesc(128, BN);
+        constexpr uint32_t idesc = make_idesc(64, BN);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -177,10 +178,10 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tc_fence_after();
-            const int row = quarter * 32 + lane;
-            const bool row_ok = row < M;
+            const int row = quarter * 16 + (lane & 15);          // M = 64 accumulator: 16 rows per TMEM lane quarter
+            const bool row_ok = lane < 16 && row < M;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            if (quarter * 32 < M) {                     // warp-uniform: quarters beyond M have nothing to store
+            if (quarter * 16 < M) {                     // warp-uniform: quarters beyond M have nothing to store
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     const int n0 = n_blk * BN + c0;
@@ -325,6 +326,7 @@ int gemm_tc_skinny_init(tw_ctx* ctx) {
     }
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<32, 64>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<64, 64>::SMEM_BYTES));
+    TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_skinny_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Sk2Cfg<128, 64>::SMEM_BYTES));
     // probe once whether the driver accepts the 3-D view (K-block stride 128 B < row stride)
     static __nv_bfloat16* probe = nullptr;
     if (!probe) {
@@ -350,6 +352,10 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     // tiles on 148 CTAs instead of 80 64-wide ones, is 12 ms per decode slower)
     static const int waves = getenv("TWB200_SK_WAVES") ? atoi(getenv("TWB200_SK_WAVES")) : 1;
     int BN = (ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
+    // the K loop of a tile costs the same for 32, 64 or 128 columns (A-operand pacing, see the header): very wide outputs (vocab
+    // head) take 128-wide tiles once 64-wide ones would need more than two passes over the SMs
+    static const int wide = getenv("TWB200_SK_WIDE") ? atoi(getenv("TWB200_SK_WIDE")) : 1;
+    if (wide && BN == 64 && ceil_div(N, 64) > 2 * ctx->sm_count) BN = 128;
     int n_groups = 1;
     if (epi.group_n > 0) {
         if (epi.group_n % 32 || N % epi.group_n || epi.mode == EPI_RESID) {
@@ -376,7 +382,9 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     // the kernel splits K in units of K blocks: make kb_per_split a multiple of KSUB by construction
     // (k_blocks_total / ksplit rounded up to whole stages)
-    if (BN == 32)
+    if (BN == 128)
+        TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<128, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<128, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
+    else if (BN == 32)
         TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<32, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<32, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));
     else
         TW_CUDA_OK(ctx, launch_k(gemm_tc_skinny_kernel<64, 64>, dim3(grid), dim3(SK2_THREADS), Sk2Cfg<64, 64>::SMEM_BYTES, st, ma, mw, M, N, K, ksplit, epi));

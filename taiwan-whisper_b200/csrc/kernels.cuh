@@ -136,7 +136,7 @@ bool absorbed_attention_supported(int H, int d);
 size_t absorbed_attention_partial_floats(int B, int H, int d);
 int absorbed_attention(tw_ctx* ctx, const __nv_bfloat16* qt, const __nv_bfloat16* enc, int Tk, int B, int H, int d, float* partial,
                        __nv_bfloat16* ctx_out, cudaStream_t st, const int32_t* active = nullptr, const int32_t* n_active = nullptr,
-                       int rev = 0, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                       int rev = 0, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, long long* trace = nullptr);
 
 // ---- token selection (select.cu)
 struct RulesDev {

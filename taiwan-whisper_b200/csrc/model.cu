@@ -838,7 +838,7 @@ bool check_model(tw_model* m, const char* fn) {
 // TWB200_ABSORB=0 keeps the per-layer K|V store (A/B knob).  Larger batches and the fp32 check mode stream the K|V store.
 bool use_absorb(const tw_model* m, int B) {
     const char* e = getenv("TWB200_ABSORB");       // read per call: tests switch it between decode calls
-    const bool env_on = !(e && strcmp(e, "0") == 0);
+    const bool env_on = e && strcmp(e, "1") == 0;  // opt-in: measured slower than the K|V stream (profiles/r02_absorbed_attention.md)
     return env_on && m->absorb_ok && m->use_tc && m->use_tc_skinny && B <= 64;
 }
 
@@ -1149,9 +1149,26 @@ int tw_debug_absorbed_attention(tw_ctx* ctx, const void* qt, const void* enc, in
     float* partial = nullptr;
     TW_CUDA_OK(ctx, cudaMalloc(&partial, absorbed_attention_partial_floats(B, H, d) * sizeof(float)));
     ctx->launches += 2;
+    long long* trace = nullptr;                  // TWB200_AB_TRACE=1: pipeline timeline of CTA 0 (clock64), printed to stderr
+    if (getenv("TWB200_AB_TRACE")) {
+        TW_CUDA_OK(ctx, cudaMalloc(&trace, 16 * 64 * sizeof(long long)));
+        TW_CUDA_OK(ctx, cudaMemset(trace, 0, 16 * 64 * sizeof(long long)));
+    }
     const int r = absorbed_attention(ctx, (const __nv_bfloat16*)qt, (const __nv_bfloat16*)enc, Tk, B, H, d, partial, (__nv_bfloat16*)out, st,
-                                     active, n_active, rev);
+                                     active, n_active, rev, nullptr, nullptr, trace);
     cudaStreamSynchronize(st);
+    if (trace) {
+        std::vector<long long> h(16 * 64);
+        cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t0 = 0;
+        for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        for (int t = 0; t < 16; ++t) {
+            fprintf(stderr, "[ab trace] tile %2d:", t);
+            for (int i = 0; i < 40; ++i) if (h[t * 64 + i]) fprintf(stderr, " %d:%lld", i, h[t * 64 + i] - t0);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     cudaFree(partial);
     if (r == TW_OK) TW_CUDA_OK(ctx, cudaGetLastError());
     return r;
