@@ -494,10 +494,10 @@ template <> struct Ld8<__nv_bfloat16> {
 
 // SA_UNR = rows in flight per warp
 template <typename T, int SA_UNR>
-__global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 3 : 1)   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave
+__global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 3 : 1)   // 3 CTAs / SM (<= 85 registers): the 5 x B grid of a 64-clip batch is one wave, and two CTAs fit next to a decode-step GEMM CTA
 self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
                              const int32_t* __restrict__ d_tk, int H, T* __restrict__ out, const int32_t* __restrict__ page_table,
-                             int pt_stride, const int32_t* __restrict__ finished) {
+                             int pt_stride, const int32_t* __restrict__ finished, int early) {
     __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
     __shared__ int32_t s_pt[SA_MAX_PAGES];
     pdl_trigger();
@@ -509,7 +509,7 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
     // so that the per-row page lookup is not a dependent global load in front of every K|V row fetch
     const bool pt_smem = page_table && pt_stride <= SA_MAX_PAGES;
     if (pt_smem && (int)threadIdx.x < pt_stride) s_pt[threadIdx.x] = page_table[(int64_t)b * pt_stride + threadIdx.x];
-    pdl_wait();                                      // q and the newest cache row come from the QKV GEMM just before
+    if (!early) pdl_wait();                          // q and the newest cache row come from the QKV GEMM just before
     if (pt_smem) __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (d_tk) Tk = *d_tk + 1;
@@ -526,47 +526,80 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
     float qf[8], of[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { qf[e] = 0.0f; of[e] = 0.0f; }
-    if (active) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qf[e] = to_f32(q[(int64_t)b * q_stride + col + e]);
-    }
     float mrun = -INFINITY, lrun = 0.0f;
-    for (int r0 = warp; r0 < Tk; r0 += SA_WARPS * SA_UNR) {
-        typename Ld8<T>::Raw kr[SA_UNR], vr[SA_UNR];
+    auto consume = [&](const typename Ld8<T>::Raw& kraw, const typename Ld8<T>::Raw& vraw) {
+        float kf[8], vf[8];
+        if (active) { Ld8<T>::unpack(kraw, kf); Ld8<T>::unpack(vraw, vf); }
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+        }
+        float dot = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot = fmaf(qf[e], kf[e], dot);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        const float m_new = fmaxf(mrun, dot);
+        const float sc = __expf(mrun - m_new);
+        const float p = __expf(dot - m_new);
+        lrun = lrun * sc + p;
+        mrun = m_new;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) of[e] = fmaf(p, vf[e], of[e] * sc);
+    };
+    // Rows of earlier positions were written by earlier steps: with `early` (decode step: Tk = position + 1 read before the wait,
+    // like the active list) the first batch of them is loaded into registers, and the later ones are pulled into L2, BEFORE the
+    // dependency wait, i.e. under the QKV GEMM that is still running (its CTAs leave room for one CTA of this kernel per SM).  Only
+    // q and the newest row depend on that GEMM.
+    const int n_old = early ? Tk - 1 : Tk;            // rows [0, n_old) may be read before the wait
+    typename Ld8<T>::Raw kr[SA_UNR], vr[SA_UNR];
+    auto load_batch = [&](int base, int lim) {
 #pragma unroll
         for (int u = 0; u < SA_UNR; ++u) {
-            const int r = r0 + u * SA_WARPS;
-            if (r < Tk && active) {
+            const int r = base + u * SA_WARPS;
+            if (r < lim && active) {
                 const T* rp = row_ptr(r);
                 kr[u] = Ld8<T>::load(rp);
                 vr[u] = Ld8<T>::load(rp + d);
             }
         }
-#pragma unroll
-        for (int u = 0; u < SA_UNR; ++u) {
-            const int r = r0 + u * SA_WARPS;
-            if (r < Tk) {                                   // warp-uniform
-                float kf[8], vf[8];
-                if (active) { Ld8<T>::unpack(kr[u], kf); Ld8<T>::unpack(vr[u], vf); }
-                else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
-                }
-                float dot = 0.0f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dot = fmaf(qf[e], kf[e], dot);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-                const float m_new = fmaxf(mrun, dot);
-                const float sc = __expf(mrun - m_new);
-                const float p = __expf(dot - m_new);
-                lrun = lrun * sc + p;
-                mrun = m_new;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) of[e] = fmaf(p, vf[e], of[e] * sc);
+    };
+    int r0 = warp, lim = n_old;
+    load_batch(r0, lim);
+    if (early) {
+        // one 128-byte line per lane: lanes 0-3 the K part of this CTA's 4 heads, lanes 4-7 the V part
+        if (lane < 8 && hg * SA_HG * HD + (lane & 3) * 64 < d) {
+            for (int r = warp + SA_UNR * SA_WARPS; r < n_old; r += SA_WARPS) {
+                const int64_t pr = ptb ? (int64_t)ptb[r / TW_KV_PAGE] * TW_KV_PAGE + r % TW_KV_PAGE : (int64_t)r;
+                const T* lp = kv + (page_table ? 0 : (int64_t)b * kv_clip_stride) + pr * 2 * d + (lane >> 2) * d + hg * SA_HG * HD + (lane & 3) * 64;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(lp));
             }
         }
+        pdl_wait();
+    }
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[e] = to_f32(q[(int64_t)b * q_stride + col + e]);
+    }
+    while (true) {
+#pragma unroll
+        for (int u = 0; u < SA_UNR; ++u)
+            if (r0 + u * SA_WARPS < lim) consume(kr[u], vr[u]);                  // warp-uniform
+        r0 += SA_WARPS * SA_UNR;
+        if (r0 >= Tk) break;
+        lim = Tk;
+        load_batch(r0, lim);
+    }
+    // early path: the newest row when it falls inside the first batch (Tk - 1 < SA_UNR * SA_WARPS), which the loop above skipped
+    if (early && Tk - 1 < SA_UNR * SA_WARPS && (Tk - 1) % SA_WARPS == warp) {
+        typename Ld8<T>::Raw k1, v1;
+        if (active) {
+            const T* rp = row_ptr(Tk - 1);
+            k1 = Ld8<T>::load(rp);
+            v1 = Ld8<T>::load(rp + d);
+        }
+        consume(k1, v1);
     }
     {
         float* rec = s_rec[warp][lane >> 3];
@@ -598,8 +631,11 @@ template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                            T* out, cudaStream_t st, const int32_t* page_table, int pt_stride, const int32_t* finished) {
     dim3 grid(ceil_div(H, SA_HG), B);
+    // early: old cache rows are fetched before the programmatic-dependency wait (only inside the decode step, where the row count
+    // comes from the device-side position and rows below it are older than the previous kernel); TWB200_SA_EARLY=0 switches it off
+    static const bool early_on = !(getenv("TWB200_SA_EARLY") && atoi(getenv("TWB200_SA_EARLY")) == 0);
     launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
-             page_table, pt_stride, finished);
+             page_table, pt_stride, finished, (early_on && d_tk) ? 1 : 0);
 }
 template void self_attention_decode<float>(const float*, int64_t, const float*, int64_t, int, const int32_t*, int, int, float*,
                                            cudaStream_t, const int32_t*, int, const int32_t*);
