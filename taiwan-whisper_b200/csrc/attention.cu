@@ -183,7 +183,11 @@ template void encoder_attention_simt<__nv_bfloat16>(const __nv_bfloat16*, __nv_b
 // per head; a small second kernel merges the records of a clip.  Record index = cta + clip (unique, <= G + B - 2).
 // Variants measured on B200 and rejected (profiles/r01_split_decode.md): the refill issued by the last warp to release a
 // stage (shared-memory counter), and warp-private rings of single-row copies — both 10-15 % slower.
-constexpr int DA_WARPS = 8;        // consumer warps == rows per stage
+constexpr int DA_WARPS = 8;        // consumer warps
+// rows per warp per stage: with two, their dot products / exponentials are independent chains.  The one-row kernel was bound by the
+// consumer warps' latency per row, not by HBM (its rate followed the number of SMs: 5.32 TB/s on 148, 4.64 on 124); with two rows it
+// is HBM-bound (5.83 TB/s on 148 SMs, 5.80 on 124).  The fp32 check mode keeps one row (its stage would not fit twice).
+template <typename T> struct DaRows { static constexpr int RPW = sizeof(T) == 2 ? 2 : 1; static constexpr int SROWS = DA_WARPS * RPW; };
 constexpr int DA_MAXSLOT = 5;      // ceil(H*8/32) with H <= 20
 constexpr int DA_PSTRIDE = HD + 2; // partial record: m, l, o[64]
 constexpr int DA_MAX_STAGES = 8;
@@ -253,9 +257,9 @@ static DaPlan da_plan(int total_rows, int H, int esz, int sm_count, int max_stag
     if (g < 1) g = 1;
     p.G = g;
     p.R = ceil_div(total_rows, g);
-    const size_t stage_bytes = (size_t)nw * 2 * H * HD * esz;
+    const size_t stage_bytes = (size_t)nw * (esz == 2 ? 2 : 1) * 2 * H * HD * esz;
     const size_t merge_bytes = (size_t)nw * H * DA_PSTRIDE * sizeof(float);
-    int st = (int)((200 * 1024 - merge_bytes) / stage_bytes);
+    int st = (int)((220 * 1024 - merge_bytes) / stage_bytes);
     if (st > DA_MAX_STAGES) st = DA_MAX_STAGES;
     if (st > max_stages) st = max_stages;
     if (st < 2) st = 2;
@@ -271,10 +275,11 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                         const int32_t* __restrict__ d_tk, int B, int H, int stages, int kv_static, float* __restrict__ partial,
                         const int32_t* __restrict__ active, const int32_t* __restrict__ n_active) {
     constexpr int NW = DA_WARPS;
+    constexpr int DA_RPW = DaRows<T>::RPW, DA_SROWS = DaRows<T>::SROWS;
     extern __shared__ __align__(128) unsigned char da_raw[];
     const int d = H * HD;
     const int row_elems = 2 * d;
-    const uint32_t stage_bytes = (uint32_t)NW * row_elems * sizeof(T);
+    const uint32_t stage_bytes = (uint32_t)DA_SROWS * row_elems * sizeof(T);
     T* ring = reinterpret_cast<T*>(da_raw);
     float* merge = reinterpret_cast<float*>(da_raw + (size_t)stages * stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(da_raw + (size_t)stages * stage_bytes + (size_t)NW * H * DA_PSTRIDE * sizeof(float));
@@ -319,8 +324,8 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                 const int b = (int)(r / Tk);                         // slot in the row stream
                 const int64_t seg_end = min(row_end, (int64_t)(b + 1) * Tk);
                 const T* src_clip = kv + (int64_t)(active ? active[b] : b) * kv_clip_stride;
-                for (int64_t r0 = r; r0 < seg_end; r0 += NW) {
-                    const int nrows = (int)min((int64_t)NW, seg_end - r0);
+                for (int64_t r0 = r; r0 < seg_end; r0 += DA_SROWS) {
+                    const int nrows = (int)min((int64_t)DA_SROWS, seg_end - r0);
                     da_mbar_wait(da_smem_u32(&empty_bar[stage]), phase ^ 1);
                     const uint32_t bytes = (uint32_t)nrows * row_elems * sizeof(T);
                     const uint32_t fb = da_smem_u32(&full_bar[stage]);
@@ -358,37 +363,51 @@ decode_attention_stream(const T* __restrict__ q, int64_t q_stride, const T* __re
                 for (int e = 0; e < 8; ++e) qf[s][e] = to_f32(qb[slot * 8 + e]);
             }
         }
-        for (int64_t r0 = r; r0 < seg_end; r0 += NW) {
-            const int nrows = (int)min((int64_t)NW, seg_end - r0);
+        for (int64_t r0 = r; r0 < seg_end; r0 += DA_SROWS) {
+            const int nrows = (int)min((int64_t)DA_SROWS, seg_end - r0);
             da_mbar_wait(da_smem_u32(&full_bar[stage]), phase);
             if (warp < nrows) {
-                const T* row = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)stage * stage_bytes) +
-                               (size_t)warp * row_elems;
+                // this warp's rows of the stage: warp and warp + DA_WARPS (the second one may be past the segment)
+                const T* row0 = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)stage * stage_bytes) +
+                                (size_t)warp * row_elems;
+                const T* row1 = row0 + (size_t)DA_WARPS * row_elems;
+                const bool two = DA_RPW == 2 && warp + DA_WARPS < nrows;   // warp-uniform
                 // math is unconditional (idle slots carry zeros) so the shuffles stay warp-converged
 #pragma unroll
                 for (int s = 0; s < DA_MAXSLOT; ++s) {
                     const int slot = lane + 32 * s;
-                    float kf[8], vf[8];
+                    float k0[8], v0[8], k1[8], v1[8];
                     if (slot < nslots) {
-                        Vec8<T>::load_shared(row + slot * 8, kf);
-                        Vec8<T>::load_shared(row + d + slot * 8, vf);
+                        Vec8<T>::load_shared(row0 + slot * 8, k0);
+                        Vec8<T>::load_shared(row0 + d + slot * 8, v0);
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+                        for (int e = 0; e < 8; ++e) { k0[e] = 0.0f; v0[e] = 0.0f; }
                     }
-                    float dot = 0.0f;
+                    if (two && slot < nslots) {
+                        Vec8<T>::load_shared(row1 + slot * 8, k1);
+                        Vec8<T>::load_shared(row1 + d + slot * 8, v1);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) dot = fmaf(qf[s][e], kf[e], dot);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-                    const float m_new = fmaxf(mrun[s], dot);
+                        for (int e = 0; e < 8; ++e) { k1[e] = 0.0f; v1[e] = 0.0f; }
+                    }
+                    float dot0 = 0.0f, dot1 = 0.0f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { dot0 = fmaf(qf[s][e], k0[e], dot0); dot1 = fmaf(qf[s][e], k1[e], dot1); }
+                    dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1);
+                    dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1);
+                    dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
+                    dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+                    dot0 += __shfl_xor_sync(0xffffffffu, dot0, 4);
+                    dot1 += __shfl_xor_sync(0xffffffffu, dot1, 4);
+                    if (!two) dot1 = -INFINITY;                             // exp(-inf - m) = 0: the absent row adds nothing
+                    const float m_new = fmaxf(mrun[s], fmaxf(dot0, dot1));
                     const float sc = __expf(mrun[s] - m_new);     // exp(-inf) = 0 on the first row
-                    const float p = __expf(dot - m_new);
-                    lrun[s] = lrun[s] * sc + p;
+                    const float p0 = __expf(dot0 - m_new), p1 = __expf(dot1 - m_new);
+                    lrun[s] = lrun[s] * sc + (p0 + p1);
                     mrun[s] = m_new;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) of[s][e] = fmaf(p, vf[e], of[s][e] * sc);
+                    for (int e = 0; e < 8; ++e) of[s][e] = fmaf(p1, v1[e], fmaf(p0, v0[e], of[s][e] * sc));
                 }
             }
             __syncwarp();

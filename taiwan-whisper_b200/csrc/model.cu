@@ -881,6 +881,7 @@ int tw_ctx_create(int device, tw_ctx** out) {
         return TW_E_UNSUPPORTED;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (getenv("TWB200_SM_LIMIT")) ctx->sm_count = atoi(getenv("TWB200_SM_LIMIT"));       // experiment: persistent grids on fewer SMs
     TW_CHECK(logmel_init(ctx));
     TW_CHECK(gemm_tc_init(ctx));
     TW_CHECK(gemm_tc_skinny_init(ctx));
