@@ -151,6 +151,26 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
                        const int32_t* prompt, int P, const tw_rules* rules, int max_length,
                        int32_t* out_tokens_host, int32_t* out_lengths_host, void* stream);
 
+/* Two-stage pipeline over SM partitions: the batch loop of the reference (ref training/run_pseudo_labelling.py:915-918,
+ * `for step, (batch, file_ids) in enumerate(...): generated_ids = generate_fn(batch["input_features"], **gen_kwargs)`) handles one
+ * batch at a time; here the front end + encoder + cross-K/V of batch i+1 run concurrently with the greedy decode of batch i.  The decode
+ * is HBM-bound and runs as fast on ~5/6 of the SMs; the encoder is tensor-bound and needs little HBM bandwidth.  The GPU is split into
+ * two CUDA green contexts (driver-level SM partitions); stage 1 runs in the small one, stage 2 in the rest.
+ *   tw_pipeline_enable   n_enc_sms SMs (8 .. half the device; the driver rounds to its granularity) for stage 1; allocates the second
+ *                        encoder-output / K|V-store pair.  TW_E_UNSUPPORTED when the driver has no green contexts.
+ *   tw_pipeline_encode   ASYNCHRONOUS stage 1 of a batch into slot 0 / 1: copy of int16 PCM [B, 480000] (host — it must stay valid until
+ *                        the matching tw_pipeline_decode returns — or device), log-mel, encoder, cross-K/V.  Waits (on the device)
+ *                        for the decode that last used the slot.
+ *   tw_pipeline_decode   stage 2 of the batch in `slot`: greedy decode, ids to HOST buffers, synchronised on return
+ *                        (arguments as tw_transcribe_host).
+ * Use: encode(b0, 0); for i: { encode(b[i+1], (i+1)&1); decode(i&1) -> ids of b[i] }.  Ids equal tw_transcribe_host's up to the
+ * bf16 rounding of a different row split of the K|V stream. */
+TW_API int tw_pipeline_enable(tw_model* m, int n_enc_sms);
+TW_API int tw_pipeline_info(const tw_model* m, int* n_enc_sms, int* n_dec_sms);
+TW_API int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot);
+TW_API int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int P, const tw_rules* rules, int max_length,
+                              int32_t* out_tokens_host, int32_t* out_lengths_host);
+
 /* Per-stage device time of the last tw_transcribe_host / tw_decode_greedy call in ms (CUDA events on the call's
  * stream): [0] log-mel, [1] encoder, [2] cross-K/V, [3] decode (incl. the D2H of the ids), [4] total, [5] H2D copy. */
 TW_API int tw_last_stage_ms(tw_model* m, float out_ms[6]);

@@ -661,15 +661,21 @@ template void self_attention_decode<float>(const float*, int64_t, const float*, 
 template void self_attention_decode<__nv_bfloat16>(const __nv_bfloat16*, int64_t, const __nv_bfloat16*, int64_t, int, const int32_t*,
                                                    int, int, __nv_bfloat16*, cudaStream_t, const int32_t*, int, const int32_t*);
 
-static int g_da_sm_count = 0;
+static int g_da_sm_dev = 0;       // SMs of the device: sizes the partial-record workspace
+static int g_da_sm_count = 0;     // CTAs of the stream kernel = SMs the launching stream may use (decode_attention_set_sms)
 size_t decode_attention_partial_floats(int B, int H) {
-    if (g_da_sm_count == 0) {
+    if (g_da_sm_dev == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_da_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_da_sm_count <= 0) g_da_sm_count = 148;
+        cudaDeviceGetAttribute(&g_da_sm_dev, cudaDevAttrMultiProcessorCount, dev);
+        if (g_da_sm_dev <= 0) g_da_sm_dev = 148;
+        if (g_da_sm_count == 0) g_da_sm_count = g_da_sm_dev;
     }
-    return (size_t)(g_da_sm_count + B) * H * DA_PSTRIDE;
+    return (size_t)(g_da_sm_dev + B) * H * DA_PSTRIDE;
+}
+void decode_attention_set_sms(int n) {
+    (void)decode_attention_partial_floats(1, 1);
+    g_da_sm_count = (n > 0 && n < g_da_sm_dev) ? n : g_da_sm_dev;
 }
 
 template <typename T>

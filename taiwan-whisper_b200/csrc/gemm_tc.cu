@@ -404,7 +404,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
-static int g_sm_count = 148;
 
 using MapKey = std::tuple<const void*, int64_t, int64_t, int64_t, int, int>;
 static std::map<MapKey, CUtensorMap> g_maps;     // per process; a ctx is per device per process
@@ -420,7 +419,6 @@ int gemm_tc_init(tw_ctx* ctx) {
         }
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    g_sm_count = ctx->sm_count;
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));
     TW_CUDA_OK(ctx, cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES));
@@ -465,7 +463,7 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     }
     // skinny (decode, M <= 128): the GEMM streams W once; narrow N tiles spread it over many SMs
     // (N tiles of 32 unless that gives more tiles than SMs, then 64 so that one wave covers the matrix)
-    const int BN = (M <= TC_BM) ? ((ceil_div(N, 32) > g_sm_count) ? 64 : 32) : ((N > 128) ? 256 : 128);
+    const int BN = (M <= TC_BM) ? ((ceil_div(N, 32) > ctx->sm_count) ? 64 : 32) : ((N > 128) ? 256 : 128);
     CUtensorMap ma, mw, mc;
     TW_CHECK(get_map(ctx, A, M, K, lda, TC_BM, &ma));
     TW_CHECK(get_map(ctx, W, N, K, ldw, BN, &mw));
@@ -483,13 +481,13 @@ int gemm_tc(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_bfloat1
     if (BN <= 64 && epi.mode == EPI_RESID) {
         // skinny residual GEMM: split K so that ~one wave of CTAs each streams a short K range
         const int kb = ceil_div(K, TC_BK);
-        ksplit = g_sm_count / tiles;
+        ksplit = ctx->sm_count / tiles;
         if (ksplit > kb / 4) ksplit = kb / 4;
         if (ksplit < 1) ksplit = 1;
         ksplit = ceil_div(kb, ceil_div(kb, ksplit));        // every split gets at least one K block
     }
     tiles *= ksplit;
-    const int grid = tiles < g_sm_count ? tiles : g_sm_count;
+    const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     if (BN == 256)
         TW_CUDA_OK(ctx, launch_k(gemm_tc_kernel<256>, dim3(grid), dim3(TC_THREADS), TcCfg<256>::SMEM_BYTES, st, ma, mw, mc, M, N, K, ksplit, epi));
     else if (BN == 64)

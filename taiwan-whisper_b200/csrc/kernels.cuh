@@ -121,6 +121,8 @@ void decode_attention(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip
                       float* partial, T* out, cudaStream_t st, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr,
                       const int32_t* active = nullptr, const int32_t* n_active = nullptr);
 size_t decode_attention_partial_floats(int B, int H);
+// the K|V stream kernel launches one CTA per SM: n = SMs of the partition its stream runs in (0 = the whole device)
+void decode_attention_set_sms(int n);
 // single-launch self-attention over the short decoder cache (Tk = *d_tk + 1 when d_tk is given)
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,

@@ -6,6 +6,7 @@
 //   log-mel (K1) -> conv stem as im2col + GEMM with fused GELU(+positions) -> L_enc x {LN, QKV GEMM,
 //   attention, out-proj GEMM (+residual), LN, fc1 GEMM (+GELU), fc2 GEMM (+residual)} -> LN
 //   -> cross-attention K/V for every decoder layer (once per window) -> greedy loop on the device.
+#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -85,9 +86,11 @@ struct LayerW {
 struct GraphKey {
     int B, eos, pad, ts_begin, no_ts, max_init, budget;
     const void* enc;       // the absorbed cross-attention reads the encoder output directly: the graph bakes the pointer in
+    const void* xkv;       // K|V store of the call (the pipeline alternates between two)
+    int sms;               // SMs the step was sized for (and, under the pipeline, the partition the graph was captured in)
     bool operator<(const GraphKey& o) const {
-        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, budget, enc) <
-               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.budget, o.enc);
+        return std::tie(B, eos, pad, ts_begin, no_ts, max_init, budget, enc, xkv, sms) <
+               std::tie(o.B, o.eos, o.pad, o.ts_begin, o.no_ts, o.max_init, o.budget, o.enc, o.xkv, o.sms);
     }
 };
 struct GraphEntry {
@@ -145,6 +148,20 @@ struct tw_model {
     bool use_graph = true;       // replay one captured CUDA graph per decode step
     bool use_pdl = true;         // programmatic dependent launch inside the decode step
     cudaStream_t cap_stream = nullptr;
+    // Two-stage pipeline over SM partitions (tw_pipeline_*): the front end + encoder + cross-K/V of batch i+1 run in a small green
+    // context while the decode of batch i runs in the rest of the GPU.  Decode is HBM-bound and does not need every SM (its time
+    // is the same on 124 as on 148); the encoder is tensor-bound and needs almost no HBM bandwidth.
+    struct Pipeline {
+        bool on = false;
+        int n_enc = 0, n_dec = 0, n_dev = 0;
+        CUgreenCtx g_enc = nullptr, g_dec = nullptr;
+        cudaStream_t s_enc = nullptr, s_dec = nullptr, s_cap = nullptr;    // s_cap: graph capture inside the decode partition
+        void* enc_out[2] = {nullptr, nullptr};
+        void* xkv[2] = {nullptr, nullptr};
+        cudaEvent_t enc_done[2] = {nullptr, nullptr}, dec_done[2] = {nullptr, nullptr};
+        bool dec_pending[2] = {false, false};
+        bool in_decode = false;
+    } pipe;
     std::map<GraphKey, GraphEntry> graphs;
     double prof_bytes = 0.0;     // K|V bytes of one profiled cross-attention launch
     // debug timeline (TWB200_TRACE=<position>): CUDA events after every kernel of two middle decoder layers at that
@@ -155,8 +172,8 @@ struct tw_model {
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;   // pairs
     int prof_used = 0;
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6]: before the H2D copy
-    bool ev_valid[7] = {false, false, false, false, false, false, false};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [6]: before the H2D copy, [7]: decode start (pipeline)
+    bool ev_valid[8] = {false, false, false, false, false, false, false, false};
 };
 
 namespace {
@@ -744,7 +761,7 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
     if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
     GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, m->row_budget_on ? 1 : 0,
-                 m->absorb_now ? m->cur_enc : nullptr};
+                 m->absorb_now ? m->cur_enc : nullptr, m->xkv, ctx->sm_count};
     cudaGraphExec_t exec = nullptr;
     uint64_t exec_kernels = 0;
 
@@ -762,9 +779,11 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
                 // capture one step on the model's private stream (nothing executes during capture)
                 cudaGraph_t graph = nullptr;
                 const uint64_t l0 = ctx->launches;
-                TW_CUDA_OK(ctx, cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-                int rc = launch_step<T>(m, B, R, S, io, m->cap_stream);
-                cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
+                // kernel nodes run in the context of the CAPTURE stream: under the pipeline that must be the decode partition
+                cudaStream_t cap = m->pipe.in_decode ? m->pipe.s_cap : m->cap_stream;
+                TW_CUDA_OK(ctx, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+                int rc = launch_step<T>(m, B, R, S, io, cap);
+                cudaError_t ce = cudaStreamEndCapture(cap, &graph);
                 if (rc != TW_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 if (ce != cudaSuccess || !graph) {
                     ctx->set_error(TW_E_CUDA, std::string("decode graph capture failed: ") + cudaGetErrorString(ce));
@@ -957,6 +976,22 @@ void tw_model_free(tw_model* m) {
     if (m->h_page_table) cudaFreeHost(m->h_page_table);
     for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
     if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+    if (m->pipe.on) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 2; ++i) {
+            if (m->pipe.enc_done[i]) cudaEventDestroy(m->pipe.enc_done[i]);
+            if (m->pipe.dec_done[i]) cudaEventDestroy(m->pipe.dec_done[i]);
+        }
+        for (cudaStream_t s : {m->pipe.s_enc, m->pipe.s_dec, m->pipe.s_cap})
+            if (s) cudaStreamDestroy(s);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && fn) {
+            auto destroy = reinterpret_cast<CUresult (*)(CUgreenCtx)>(fn);
+            if (m->pipe.g_enc) destroy(m->pipe.g_enc);
+            if (m->pipe.g_dec) destroy(m->pipe.g_dec);
+        }
+    }
     for (auto& ev : m->ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : m->prof_ev) cudaEventDestroy(ev);
@@ -1059,7 +1094,7 @@ int tw_decode_greedy(tw_model* m, const void* enc_out, int B, const int32_t* pro
             : decode_impl<float>(m, B, prompt, P, R, max_length, out_tokens, out_lengths, forced, logits_tap, tap_steps, st);
     cudaEventRecord(m->ev[4], st);
     m->ev_valid[2] = m->ev_valid[3] = m->ev_valid[4] = true;
-    m->ev_valid[0] = m->ev_valid[1] = m->ev_valid[6] = false;
+    m->ev_valid[0] = m->ev_valid[1] = m->ev_valid[6] = m->ev_valid[7] = false;
     return r;
 }
 
@@ -1130,6 +1165,179 @@ int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_t* n_va
     TW_CUDA_OK(ctx, cudaStreamSynchronize(st));
     for (int i = 0; i < 5; ++i) m->ev_valid[i] = true;
     m->ev_valid[6] = true;
+    m->ev_valid[7] = false;
+    return TW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pipeline over SM partitions
+namespace {
+typedef CUresult (*PfnGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType);
+typedef CUresult (*PfnSmSplit)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+typedef CUresult (*PfnGenDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+typedef CUresult (*PfnGreenCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*PfnGreenStream)(CUstream*, CUgreenCtx, unsigned int, int);
+void* driver_entry(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return fn;
+}
+// every persistent grid of the library is sized from these two numbers
+void set_active_sms(tw_model* m, int n) {
+    m->ctx->sm_count = n;
+    decode_attention_set_sms(n);
+}
+}  // namespace
+
+int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
+    if (!check_model(m, "tw_pipeline_enable")) return TW_E_INVALID;
+    tw_ctx* ctx = m->ctx;
+    if (m->pipe.on) return TW_OK;
+    auto pGetRes = reinterpret_cast<PfnGetDevResource>(driver_entry("cuDeviceGetDevResource"));
+    auto pSplit = reinterpret_cast<PfnSmSplit>(driver_entry("cuDevSmResourceSplitByCount"));
+    auto pDesc = reinterpret_cast<PfnGenDesc>(driver_entry("cuDevResourceGenerateDesc"));
+    auto pCreate = reinterpret_cast<PfnGreenCreate>(driver_entry("cuGreenCtxCreate"));
+    auto pStream = reinterpret_cast<PfnGreenStream>(driver_entry("cuGreenCtxStreamCreate"));
+    if (!pGetRes || !pSplit || !pDesc || !pCreate || !pStream) {
+        ctx->set_error(TW_E_UNSUPPORTED, "tw_pipeline_enable: this driver has no green contexts (SM partitions)");
+        return TW_E_UNSUPPORTED;
+    }
+    auto& P = m->pipe;
+    CUdevResource all, small, rest;
+    auto fail = [&](const char* what, CUresult r) {
+        ctx->set_error(TW_E_CUDA, std::string("tw_pipeline_enable: ") + what + " failed (" + std::to_string((int)r) + ")");
+        return TW_E_CUDA;
+    };
+    CUresult r = pGetRes((CUdevice)ctx->device, &all, CU_DEV_RESOURCE_TYPE_SM);
+    if (r != CUDA_SUCCESS) return fail("cuDeviceGetDevResource", r);
+    P.n_dev = (int)all.sm.smCount;
+    if (n_enc_sms < 8 || n_enc_sms > P.n_dev / 2) {
+        ctx->set_error(TW_E_INVALID, "tw_pipeline_enable: the encoder partition needs between 8 SMs and half of the device");
+        return TW_E_INVALID;
+    }
+    unsigned nb = 1;
+    r = pSplit(&small, &nb, &all, &rest, 0, (unsigned)n_enc_sms);
+    if (r != CUDA_SUCCESS || nb != 1) return fail("cuDevSmResourceSplitByCount", r);
+    P.n_enc = (int)small.sm.smCount;
+    P.n_dec = (int)rest.sm.smCount;
+    CUdevResourceDesc d_small, d_rest;
+    if ((r = pDesc(&d_small, &small, 1)) != CUDA_SUCCESS || (r = pDesc(&d_rest, &rest, 1)) != CUDA_SUCCESS) return fail("cuDevResourceGenerateDesc", r);
+    if ((r = pCreate(&P.g_enc, d_small, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) return fail("cuGreenCtxCreate", r);
+    if ((r = pCreate(&P.g_dec, d_rest, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) return fail("cuGreenCtxCreate", r);
+    CUstream se, sd, sc;
+    if ((r = pStream(&se, P.g_enc, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS || (r = pStream(&sd, P.g_dec, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS ||
+        (r = pStream(&sc, P.g_dec, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS)
+        return fail("cuGreenCtxStreamCreate", r);
+    P.s_enc = (cudaStream_t)se;
+    P.s_dec = (cudaStream_t)sd;
+    P.s_cap = (cudaStream_t)sc;
+    // second set of the buffers the two stages hand over: encoder output and cross-attention K|V store
+    const tw_model_desc& D = m->desc;
+    const size_t M = (size_t)D.max_batch * TW_N_CTX, d = D.d_model, e = m->esz;
+    P.enc_out[0] = m->ws_enc;
+    P.xkv[0] = m->xkv;
+    TW_CHECK(dev_alloc(m, &P.enc_out[1], M * d * e));
+    TW_CHECK(dev_alloc(m, &P.xkv[1], (size_t)D.dec_layers * M * 2 * d * e));
+    for (int i = 0; i < 2; ++i) {
+        TW_CUDA_OK(ctx, cudaEventCreateWithFlags(&P.enc_done[i], cudaEventDisableTiming));
+        TW_CUDA_OK(ctx, cudaEventCreateWithFlags(&P.dec_done[i], cudaEventDisableTiming));
+    }
+    P.on = true;
+    return TW_OK;
+}
+
+int tw_pipeline_info(const tw_model* m, int* n_enc_sms, int* n_dec_sms) {
+    if (!m) return TW_E_INVALID;
+    if (n_enc_sms) *n_enc_sms = m->pipe.on ? m->pipe.n_enc : 0;
+    if (n_dec_sms) *n_dec_sms = m->pipe.on ? m->pipe.n_dec : 0;
+    return TW_OK;
+}
+
+int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot) {
+    if (!check_model(m, "tw_pipeline_encode")) return TW_E_INVALID;
+    tw_ctx* ctx = m->ctx;
+    auto& P = m->pipe;
+    if (!P.on || slot < 0 || slot > 1 || B <= 0 || B > m->desc.max_batch || !pcm) {
+        ctx->set_error(TW_E_INVALID, "tw_pipeline_encode: pipeline not enabled, bad slot (0 / 1), bad batch or null buffer");
+        return TW_E_INVALID;
+    }
+    const tw_model_desc& D = m->desc;
+    cudaStream_t st = P.s_enc;
+    // the decode that last read this slot's encoder output / K|V store must have finished
+    if (P.dec_pending[slot]) TW_CUDA_OK(ctx, cudaStreamWaitEvent(st, P.dec_done[slot], 0));
+    const int sms_before = ctx->sm_count;
+    set_active_sms(m, P.n_enc);
+    void* const xkv_before = m->xkv;
+    m->xkv = P.xkv[slot];
+    int r = TW_OK;
+    do {
+        cudaEventRecord(m->ev[6], st);
+        if (cudaMemcpyAsync(m->ws_pcm, pcm, (size_t)B * TW_N_SAMPLES * sizeof(int16_t), cudaMemcpyDefault, st) != cudaSuccess) { r = TW_E_CUDA; break; }
+        const int32_t* nv = nullptr;
+        if (n_valid_host) {
+            if (cudaMemcpyAsync(m->ws_nvalid, n_valid_host, B * sizeof(int32_t), cudaMemcpyDefault, st) != cudaSuccess) { r = TW_E_CUDA; break; }
+            nv = m->ws_nvalid;
+        }
+        cudaEventRecord(m->ev[0], st);
+        const float* clip_max = nullptr;
+        if ((r = logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st, false, &clip_max)) != TW_OK) break;
+        cudaEventRecord(m->ev[1], st);
+        r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, P.enc_out[slot], -1, nullptr, st, clip_max)
+                               : encode_impl<float>(m, m->ws_mel, B, P.enc_out[slot], -1, nullptr, st, clip_max);
+        if (r != TW_OK) break;
+        cudaEventRecord(m->ev[2], st);
+        if (!use_absorb(m, B))
+            r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, P.enc_out[slot], B, st) : cross_kv_impl<float>(m, P.enc_out[slot], B, st);
+        if (r != TW_OK) break;
+        cudaEventRecord(m->ev[3], st);
+        if (cudaEventRecord(P.enc_done[slot], st) != cudaSuccess) { r = TW_E_CUDA; break; }
+    } while (0);
+    m->xkv = xkv_before;
+    set_active_sms(m, sms_before);
+    if (r == TW_E_CUDA && ctx->err_code != TW_E_CUDA) ctx->set_error(TW_E_CUDA, std::string("tw_pipeline_encode: ") + cudaGetErrorString(cudaGetLastError()));
+    return r;
+}
+
+int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int P_len, const tw_rules* rules, int max_length,
+                       int32_t* out_tokens_host, int32_t* out_lengths_host) {
+    if (!check_model(m, "tw_pipeline_decode")) return TW_E_INVALID;
+    TW_CHECK(check_decode_args(m, B, prompt, P_len, rules, max_length));
+    tw_ctx* ctx = m->ctx;
+    auto& P = m->pipe;
+    if (!P.on || slot < 0 || slot > 1 || !out_tokens_host || !out_lengths_host) {
+        ctx->set_error(TW_E_INVALID, "tw_pipeline_decode: pipeline not enabled, bad slot (0 / 1) or null buffer");
+        return TW_E_INVALID;
+    }
+    const tw_model_desc& D = m->desc;
+    cudaStream_t st = P.s_dec;
+    const int n_gen = max_length - P_len;
+    RulesDev R;
+    TW_CHECK(upload_rules(m, rules, &R, st));
+    TW_CUDA_OK(ctx, cudaStreamWaitEvent(st, P.enc_done[slot], 0));
+    const int sms_before = ctx->sm_count;
+    set_active_sms(m, P.n_dec);
+    void* const xkv_before = m->xkv;
+    m->xkv = P.xkv[slot];
+    m->cur_enc = P.enc_out[slot];
+    m->absorb_now = use_absorb(m, B);
+    P.in_decode = true;
+    cudaEventRecord(m->ev[7], st);
+    int r = D.dtype == TW_BF16
+                ? decode_impl<__nv_bfloat16>(m, B, prompt, P_len, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st)
+                : decode_impl<float>(m, B, prompt, P_len, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st);
+    P.in_decode = false;
+    m->xkv = xkv_before;
+    set_active_sms(m, sms_before);
+    if (r != TW_OK) return r;
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(out_tokens_host, m->d_out_tok, (size_t)B * n_gen * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    TW_CUDA_OK(ctx, cudaMemcpyAsync(out_lengths_host, m->d_out_len, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    cudaEventRecord(m->ev[4], st);
+    TW_CUDA_OK(ctx, cudaEventRecord(P.dec_done[slot], st));
+    P.dec_pending[slot] = true;
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    for (int i = 0; i < 5; ++i) m->ev_valid[i] = true;
+    m->ev_valid[6] = m->ev_valid[7] = true;
     return TW_OK;
 }
 
@@ -1336,13 +1544,16 @@ int tw_last_stage_ms(tw_model* m, float out_ms[6]) {
     for (int i = 0; i < 6; ++i) out_ms[i] = 0.0f;
     for (int i = 0; i < 4; ++i)
         if (m->ev_valid[i] && m->ev_valid[i + 1]) {
-            if (cudaEventSynchronize(m->ev[i + 1]) == cudaSuccess) cudaEventElapsedTime(&out_ms[i], m->ev[i], m->ev[i + 1]);
+            // under the pipeline the decode stage starts at its own event (the stages run on different streams)
+            cudaEvent_t a = (i == 3 && m->ev_valid[7]) ? m->ev[7] : m->ev[i];
+            if (cudaEventSynchronize(m->ev[i + 1]) == cudaSuccess && cudaEventSynchronize(a) == cudaSuccess)
+                cudaEventElapsedTime(&out_ms[i], a, m->ev[i + 1]);
         }
     if (m->ev_valid[6] && m->ev_valid[0]) cudaEventElapsedTime(&out_ms[5], m->ev[6], m->ev[0]);
     int first = m->ev_valid[6] ? 6 : -1;
     for (int i = 0; i < 5 && first < 0; ++i)
         if (m->ev_valid[i]) first = i;
-    if (first >= 0 && first != 4 && m->ev_valid[4]) cudaEventElapsedTime(&out_ms[4], m->ev[first], m->ev[4]);
+    if (first >= 0 && first != 4 && m->ev_valid[4] && !m->ev_valid[7]) cudaEventElapsedTime(&out_ms[4], m->ev[first], m->ev[4]);
     return TW_OK;
 }
 

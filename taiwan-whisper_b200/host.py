@@ -609,6 +609,65 @@ class B200WhisperForConditionalGeneration:
         del keep
         return out_tokens, out_lengths
 
+    # ------------------------------------------------------------------ pipelined batch loop (tw_pipeline_*)
+    def enable_pipeline(self, n_enc_sms: int = 24):
+        """Splits the GPU into two SM partitions (CUDA green contexts): `n_enc_sms` SMs for the front end + encoder + cross-K/V
+        of the NEXT batch, the rest for the greedy decode of the current one (`transcribe_batches`).  Returns (encoder SMs,
+        decode SMs) as the driver granted them.  Raises NotImplementedError when the driver has no green contexts."""
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.ctx.lib.tw_pipeline_enable(C.c_void_p(self.handle), int(n_enc_sms)))
+        a, b = C.c_int(0), C.c_int(0)
+        self.ctx.check(self.ctx.lib.tw_pipeline_info(C.c_void_p(self.handle), C.byref(a), C.byref(b)))
+        self.pipeline_sms = (a.value, b.value)
+        return self.pipeline_sms
+
+    def transcribe_batches(self, batches, max_length: int, return_timestamps: bool = False, language="zh", task="transcribe"):
+        """The reference's batch loop (ref training/run_pseudo_labelling.py:915-918) as a generator: yields (tokens, lengths) — pinned
+        host int32 tensors [B, max_length - P] / [B], a fresh pair per batch — for every int16 PCM batch [B, 480000] of `batches`
+        (pinned host or device tensors), in order.  While batch i decodes, batch i+1 is already in its log-mel / encoder /
+        cross-K/V stage on the other SM partition (`enable_pipeline` first)."""
+        if not getattr(self, "pipeline_sms", None):
+            raise RuntimeError("transcribe_batches needs enable_pipeline() first")
+        prompt = self._init_tokens(language, task, return_timestamps)
+        n_gen = max_length - len(prompt)
+        if n_gen <= 0 or max_length > self.shape.max_target:
+            raise ValueError("max_length must exceed the prompt and fit max_target_positions")
+        r = self._rules(return_timestamps)
+        rules, keep = _lib.make_rules(r["suppress"], r["begin_suppress"], r["eos"], r["pad"], r["timestamp_begin"],
+                                      r["no_timestamps"], r["max_initial_ts"])
+        p = (C.c_int32 * len(prompt))(*prompt)
+        lib, h = self.ctx.lib, C.c_void_p(self.handle)
+
+        def encode(pcm, slot):
+            if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != N_SAMPLES or pcm.shape[0] > self.max_batch:
+                raise ValueError("transcribe_batches expects int16 tensors [B <= max_batch, 480000]")
+            pcm = pcm.contiguous()
+            self.ctx.check(lib.tw_pipeline_encode(h, pcm.data_ptr(), None, pcm.shape[0], slot))
+            return pcm                               # kept alive until its decode has returned
+
+        with torch.cuda.device(self.device):
+            it = iter(batches)
+            try:
+                cur = encode(next(it), 0)
+            except StopIteration:
+                return
+            i = 0
+            while cur is not None:
+                nxt = None
+                try:
+                    nxt = encode(next(it), (i + 1) & 1)
+                except StopIteration:
+                    pass
+                B = cur.shape[0]
+                out_tokens = torch.empty((B, n_gen), dtype=torch.int32).pin_memory()
+                out_lengths = torch.empty((B,), dtype=torch.int32).pin_memory()
+                self.ctx.check(lib.tw_pipeline_decode(h, i & 1, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
+                                                      out_lengths.data_ptr()))
+                yield out_tokens, out_lengths
+                cur = nxt
+                i += 1
+        del keep
+
     def set_row_budgets(self, budgets: Optional[Sequence[int]]):
         """Test / bench hook (tw_debug_set_row_budgets): row b of the following decode calls finishes after budgets[b]
         generated tokens exactly as if it had emitted EOS next; None switches it off.  Random-init weights never emit EOS,

@@ -616,6 +616,47 @@ def test_transcribe_host_path_matches_generate():
     assert ms["total"] > 0 and ms["encoder"] > 0
 
 
+@pytest.mark.parametrize("dtype_name", ["f32", "bf16"])
+def test_pipelined_batch_loop_matches_sequential(dtype_name):
+    """transcribe_batches (stage 1 of batch i+1 on a small SM partition while batch i decodes on the rest, tw_pipeline_*) returns,
+    batch by batch, what the one-call path returns: ids equal to the oracle's in fp32 check mode; in bf16 the same lengths and the
+    same ids as transcribe_pcm wherever the two free-running decodes have not parted at a near-tie (the K|V stream is split over a
+    different number of CTAs, so partial sums round differently)."""
+    _cuda()
+    from tests.gpu_common import b200_model, oracle_run
+    shape_name = "micro128"
+    max_length = 32
+    n = max_length - 4
+    pcm, mel, ora = oracle_run(shape_name, 3, 40, False)
+    m = b200_model(shape_name, dtype_name)
+    try:
+        sms = m.enable_pipeline(16)
+    except NotImplementedError as e:
+        pytest.skip(f"no green contexts on this driver: {e}")
+    assert sms[0] >= 8 and sms[0] + sms[1] <= torch.cuda.get_device_properties(0).multi_processor_count
+    host = torch.from_numpy(pcm).pin_memory()
+    # five batches: host and device inputs, a short last batch, clips in a different order per batch
+    orders = [[0, 1, 2], [2, 0, 1], [1, 2, 0], [0, 2, 1], [1, 0]]
+    batches = [host[o].pin_memory() if i % 2 == 0 else host[o].cuda() for i, o in enumerate(orders)]
+    seq = [m.transcribe_pcm(host[o].pin_memory(), max_length) for o in orders]
+    seq = [(t.clone(), l.clone()) for t, l in seq]
+    got = list(m.transcribe_batches(batches, max_length))
+    assert len(got) == len(orders)
+    for o, (toks, lens), (st, sl) in zip(orders, got, seq):
+        assert toks.shape == (len(o), n) and lens.tolist() == sl.tolist()
+        for j, b in enumerate(o):
+            if dtype_name == "f32":
+                assert toks[j].tolist() == ora[b]["tokens"][:n], (o, j)
+            else:
+                agree = (toks[j] == st[j]).float().mean().item()
+                assert toks[j, :4].tolist() == st[j, :4].tolist() and agree >= 0.5, (o, j, agree)
+    ms = m.last_stage_ms()
+    assert ms["encoder"] > 0 and ms["decode"] > 0
+    # the one-call path still works on the whole GPU afterwards
+    t2, _ = m.transcribe_pcm(host[orders[0]].pin_memory(), max_length)
+    assert t2.tolist() == seq[0][0].tolist()
+
+
 def test_generate_argument_errors():
     _cuda()
     from tests.gpu_common import b200_model
