@@ -168,7 +168,6 @@ constexpr int FA3_KV_BYTES = FA3_BK * FA_D * 2;       // 8 KB
 constexpr int FA3_STAGES = 4;
 constexpr int FA3_SMEM = 1024 + FA_TILE_BYTES + FA3_KV_BYTES * (2 * FA3_STAGES + 1) + 512;    // Q, K x4, V x4, ones
 
-template <bool Q_TMEM>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                              __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
@@ -187,8 +186,7 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     uint64_t* s_full = v_empty + FA3_STAGES;       // 2  QK^T into score buffer b done
     uint64_t* p_full = s_full + 2;                 // 2  P written over score buffer b
     uint64_t* pv_done = p_full + 2;                // 1  one phase per key tile: P V (j) has completed
-    uint64_t* q_tmem_full = pv_done + 1;           // 1  Q copied into tensor memory (Q_TMEM)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_tmem_full + 1);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -214,7 +212,6 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             fa_mbar_init(fa_smem_u32(&p_full[i]), 4);      // one arrive per softmax warp
         }
         fa_mbar_init(fa_smem_u32(pv_done), 1);
-        fa_mbar_init(fa_smem_u32(q_tmem_full), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -237,7 +234,6 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     const uint32_t tmem_S = tmem_base;            // two score buffers of 64 columns; P (bf16 pairs) over the first 32 of each
     const uint32_t tmem_O = tmem_base + 128;
     const uint32_t tmem_L = tmem_base + 192;
-    const uint32_t tmem_Q = tmem_base + 208;      // Q_TMEM: the query tile as bf16 pairs, 32 columns (A operand of Q K^T)
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -279,10 +275,8 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
                 const uint64_t q_desc = fa_desc(q_addr);
                 const uint64_t k_desc = fa_desc(fa_smem_u32(sK + st * FA3_KV_BYTES));
 #pragma unroll
-                for (int k = 0; k < FA_D / 16; ++k) {
-                    if (Q_TMEM) fa_mma_ts(tmem_S + (j & 1) * FA3_BK, tmem_Q + 8 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                    else fa_mma(tmem_S + (j & 1) * FA3_BK, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
-                }
+                for (int k = 0; k < FA_D / 16; ++k)
+                    fa_mma(tmem_S + (j & 1) * FA3_BK, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0 ? 1u : 0u);
                 fa_commit(fa_smem_u32(&k_empty[st]));
                 fa_commit(fa_smem_u32(&s_full[j & 1]));
             }
@@ -306,13 +300,21 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             }
             __syncwarp();
         };
-        fa_mbar_wait(fa_smem_u32(Q_TMEM ? q_tmem_full : q_full), 0);
-        fa_fence_after();
+        fa_mbar_wait(fa_smem_u32(q_full), 0);
         issue_qk(0);
         if (n_tiles > 1) issue_qk(1);
         for (int j = 0; j < n_tiles; ++j) {
             issue_pv(j);
-            if (j + 2 < n_tiles) issue_qk(j + 2);
+            if (j + 2 < n_tiles) {
+                // Q K^T (j+2) overwrites the score buffer whose first 32 columns are P(j), the TMEM A operand of P V (j).  Issue
+                // order alone does not protect it: consecutive tcgen05.mma overlap in the pipe, and nothing interlocks a D write
+                // with an earlier instruction's A read from tensor memory — measured as rare wrong rows (3 of 180 runs of the
+                // 20-head, 1500-key shape at 2 CTAs per SM; 0 of 450 with the wait).  A variant with the query tile in TMEM (Q K^T
+                // as a TMEM-A instruction, +2 %) kept failing 8 of 450 and was dropped.  Wait for P V (j) to complete.
+                fa_mbar_wait(fa_smem_u32(pv_done), j & 1);
+                fa_fence_after();
+                issue_qk(j + 2);
+            }
         }
     } else {
         // ===================== softmax warps 0..3: thread = query row =====================
@@ -320,24 +322,6 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float LOG2E = 1.4426950408889634f;
         float m_ref = -INFINITY;
-        if (Q_TMEM) {
-            // A tcgen05.mma whose A operand comes from shared memory is paced by A's rows (~1 cycle per row: 128 cycles for the
-            // M128 N64 K16 Q K^T step whose tensor work is 32); with A in tensor memory it is not (profiles/r02_absorbed_attention.md).
-            // Q is the same for every key tile: each row's thread copies its 128 bytes (un-swizzled) into 32 TMEM columns once.
-            fa_mbar_wait(fa_smem_u32(q_full), 0);
-            uint32_t qv[32];
-            const unsigned char* qrow = sQ + r * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 w = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
-                qv[4 * c] = w.x; qv[4 * c + 1] = w.y; qv[4 * c + 2] = w.z; qv[4 * c + 3] = w.w;
-            }
-            fa_tmem_st32(tmem_Q + lane_off, qv);
-            fa_tmem_wait_st();
-            fa_fence_before();
-            __syncwarp();
-            if (lane == 0) fa_mbar_arrive(fa_smem_u32(q_tmem_full));
-        }
         for (int j = 0; j < n_tiles; ++j) {
             const uint32_t sbuf = tmem_S + lane_off + (j & 1) * FA3_BK;
             fa_mbar_wait(fa_smem_u32(&s_full[j & 1]), (j >> 1) & 1);
@@ -428,7 +412,11 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             __syncwarp();
             if (lane == 0) fa_mbar_arrive(fa_smem_u32(&p_full[j & 1]));
         }
-        // ---- epilogue: O / L
+        // ---- epilogue: O / L.  A parity wait only tells phases of equal parity apart if the barrier is at most one phase behind:
+        // P V (n-2) may still be in flight here (nothing after tile n-2 waited for it), and then a wait for the parity of phase n-1
+        // is satisfied by phase n-3 — O and L were read one or two tiles early in ~1 % of the launches at 2 CTAs per SM.  Wait for
+        // phase n-2 first (phase n-3 is complete: Q K^T (n-1) was issued after it).
+        if (n_tiles >= 2) fa_mbar_wait(fa_smem_u32(pv_done), (n_tiles - 2) & 1);
         fa_mbar_wait(fa_smem_u32(pv_done), (n_tiles - 1) & 1);
         fa_fence_after();
         uint32_t lv;
@@ -514,8 +502,7 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
             return TW_E_CUDA;
         }
         g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
     }
     if (causal && Sq != Sk) {
         ctx->set_error(TW_E_INVALID, "attention_tc: the causal mask needs as many queries as keys");
@@ -525,13 +512,8 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
     TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
     TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, FA3_BK));
     dim3 grid(ceil_div(Sq, FA_BQ), H, B);
-    static const bool q_tmem = !(getenv("TWB200_FA_QTMEM") && atoi(getenv("TWB200_FA_QTMEM")) == 0);     // A/B knob
-    if (q_tmem)
-        TW_CUDA_OK(ctx, launch_k(encoder_attention_tc_kernel<true>, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0,
-                                 v_col0, causal ? 1 : 0));
-    else
-        TW_CUDA_OK(ctx, launch_k(encoder_attention_tc_kernel<false>, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0,
-                                 v_col0, causal ? 1 : 0));
+    TW_CUDA_OK(ctx, launch_k(encoder_attention_tc_kernel, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0,
+                             causal ? 1 : 0));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }

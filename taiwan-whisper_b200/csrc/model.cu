@@ -386,8 +386,11 @@ int alloc_workspace(tw_model* m) {
     TW_CUDA_OK(m->ctx, cudaMemset(m->dpartial, 0, partial_floats * sizeof(float)));
     TW_CHECK(dev_alloc(m, (void**)&m->dstate, (8 * B + 8) * sizeof(int32_t)));
     m->d_row_budget = m->dstate + 7 * B;
-    TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab));
-    TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab));
+    // the selection kernel reads the masks four bytes at a time: padded to whole words (pad bytes stay zero)
+    TW_CHECK(dev_alloc(m, (void**)&m->d_suppress, D.vocab + 16));
+    TW_CHECK(dev_alloc(m, (void**)&m->d_begin_suppress, D.vocab + 16));
+    TW_CUDA_OK(m->ctx, cudaMemset(m->d_suppress, 0, D.vocab + 16));
+    TW_CUDA_OK(m->ctx, cudaMemset(m->d_begin_suppress, 0, D.vocab + 16));
     TW_CHECK(dev_alloc(m, (void**)&m->d_ids_tmp, 4096 * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_out_tok, B * D.max_target * sizeof(int32_t)));
     TW_CHECK(dev_alloc(m, (void**)&m->d_out_len, B * sizeof(int32_t)));
@@ -1032,7 +1035,7 @@ size_t tw_workspace_bytes(const tw_model_desc* desc) {
                 al(M * d * e) + al(M * d * e) + al(M * ffn * e) + al(M * d * e) + al((size_t)D.dec_layers * M * 2 * d * e) +
                 al((size_t)D.dec_layers * B * kv_pages * TW_KV_PAGE * 2 * d * e) + al(B * kv_pages * sizeof(int32_t)) +
                 al(B * d * f4) + al(B * d * e) + al(B * 3 * d * e) + al(B * d * e) + al(B * d * e) + al(B * ffn * e) + al(B * ((V + 3) / 4 * 4) * f4) +
-                al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((8 * B + 8) * sizeof(int32_t)) + al(V) + al(V) +
+                al(decode_attention_partial_floats((int)B, D.heads) * f4) + al((8 * B + 8) * sizeof(int32_t)) + al(V + 16) + al(V + 16) +
                 al(4096 * sizeof(int32_t)) + al(B * D.max_target * sizeof(int32_t)) + al(B * sizeof(int32_t)) + al(STEP_INTS * sizeof(int32_t));
     if (absorb) {
         const size_t Bd = B < 64 ? B : 64;

@@ -99,31 +99,43 @@ select_tokens_kernel(const float* __restrict__ logits, int64_t ld_logits, int V,
 
     Best bt = {-INFINITY, 0x7fffffff}, bs = {-INFINITY, 0x7fffffff};
     float lm = -INFINITY, ls = 0.0f;
-    // 8 independent loads in flight per thread (the logits were just written by the vocab GEMM: L2 latency-bound)
-    constexpr int U = 8;
-    for (int base = threadIdx.x; base < V; base += SEL_THREADS * U) {
-        float raw[U];
-        bool sup[U];
+    // Four consecutive tokens per load (float4 logits, 4 mask bytes as one word each), U such groups in flight per thread, every
+    // load issued unconditionally before the first use.  The first version loaded scalars and short-circuited the two mask bytes
+    // (`suppress || (first && begin)`): the second byte load hung on the first one's result, 16 dependent L2 round trips per
+    // iteration — 36 us per token for 13 MB (ncu source page: every stall sample on the mask tests), now bandwidth-shaped.
+    // Rows are 16-byte aligned (ld_logits % 4 == 0) and padded to a multiple of 4 floats; the masks are padded likewise.
+    constexpr int U = 4;
+    const int V4 = (V + 3) >> 2;                       // groups of 4 tokens
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const uint32_t* sup4 = reinterpret_cast<const uint32_t*>(R.suppress_mask);
+    const uint32_t* beg4 = reinterpret_cast<const uint32_t*>(R.begin_suppress_mask);
+    for (int base = threadIdx.x; base < V4; base += SEL_THREADS * U) {
+        float4 raw[U];
+        uint32_t sm[U], bm[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = base + u * SEL_THREADS;
-            raw[u] = -INFINITY;
-            sup[u] = true;
-            if (i < V) {
-                raw[u] = __ldg(row + i);
-                sup[u] = (__ldg(R.suppress_mask + i) != 0) || (first && __ldg(R.begin_suppress_mask + i) != 0);
-            }
+            const int g = min(base + u * SEL_THREADS, V4 - 1);      // clamped: the duplicate group is skipped below
+            raw[u] = __ldg(row4 + g);
+            sm[u] = __ldg(sup4 + g);
+            bm[u] = __ldg(beg4 + g);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = base + u * SEL_THREADS;
-            if (i >= V) continue;
-            const float v = masked_score(raw[u], sup[u], i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
-            if (i < split) {
-                bt = better(bt, Best{v, i});
-            } else {
-                bs = better(bs, Best{v, i});
-                if (v > -INFINITY) lse_merge(lm, ls, v, 1.0f);
+            const int g = base + u * SEL_THREADS;
+            if (g >= V4) continue;
+            const uint32_t mask = first ? (sm[u] | bm[u]) : sm[u];
+            const float r4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * g + j;
+                if (i >= V) continue;
+                const float v = masked_score(r4[j], ((mask >> (8 * j)) & 0xffu) != 0, i, R, first, ts_mode, last_ts, pen_ts, ts_forbid_end);
+                if (i < split) {
+                    bt = better(bt, Best{v, i});
+                } else {
+                    bs = better(bs, Best{v, i});
+                    if (v > -INFINITY) lse_merge(lm, ls, v, 1.0f);
+                }
             }
         }
     }

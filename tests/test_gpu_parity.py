@@ -189,6 +189,32 @@ def test_encoder_attention_kernels_vs_torch(B, S, H, impl):
     assert err < 2e-2, err                       # bf16 P and bf16 output rounding
 
 
+def test_encoder_attention_tc_repeated_runs():
+    """The tcgen05 flash kernel at the shape that puts two CTAs on most SMs (20 heads x 1500 keys), 150 runs on fresh inputs:
+    every run within tolerance.  Regression test for hazards between tcgen05 instructions on aliased tensor-memory columns
+    (P V (j) reading P(j) while Q K^T (j+2) overwrites the score buffer it lives in), which corrupted a few rows in a few
+    per cent of the launches."""
+    _cuda()
+    from taiwan_whisper_b200 import lib as twlib
+    ctx = twlib.Context.get(torch.cuda.current_device())
+    B, S, H = 1, 1500, 20
+    d = H * 64
+    bad = []
+    for it in range(150):
+        g = torch.Generator(device="cuda").manual_seed(1000 + it)
+        qkv = torch.randn((B * S, 3 * d), device="cuda", generator=g)
+        qkv[:, :d] *= 0.3
+        qkv = qkv.bfloat16()
+        out = torch.zeros((B * S, d), device="cuda", dtype=torch.bfloat16)
+        ctx.check(ctx.lib.tw_debug_encoder_attention(ctx.handle, qkv.data_ptr(), out.data_ptr(), B, S, H, twlib.TW_BF16, 1,
+                                                     torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        err = (out.float() - _attn_ref(qkv, B, S, H)).abs().max().item()
+        if err >= 2e-2:
+            bad.append((it, err))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("B,Sq,Sk,H,causal", [(3, 70, 70, 2, True), (2, 300, 300, 2, True), (1, 128, 128, 6, True),
                                               (3, 70, 1500, 6, False), (2, 129, 200, 2, False), (1, 448, 1500, 20, False)])
 @pytest.mark.parametrize("impl,dtype", [(0, "f32"), (0, "bf16"), (1, "bf16")])
@@ -628,7 +654,7 @@ def test_pipelined_batch_loop_matches_sequential(dtype_name):
     max_length = 32
     n = max_length - 4
     pcm, mel, ora = oracle_run(shape_name, 3, 40, False)
-    m = b200_model(shape_name, dtype_name)
+    m = b200_model.__wrapped__(shape_name, dtype_name)       # a private model: enabling the pipeline allocates the second buffer set
     try:
         sms = m.enable_pipeline(16)
     except NotImplementedError as e:
