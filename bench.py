@@ -51,7 +51,10 @@ def parse():
     ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-length variant (finished rows leave the K|V stream)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="headline = the sequential batch loop (default: stage 1 of batch i+1 overlaps the decode of batch i on SM partitions)")
-    ap.add_argument("--pipeline-sms", type=int, default=16, help="SMs of the front-end / encoder partition of the pipeline")
+    ap.add_argument("--pipeline-sms", type=int, default=0, help="SMs of the front-end / encoder partition of the pipeline (0 = 16 unmerged, 24 merged)")
+    ap.add_argument("--merge", type=int, default=3,
+                    help="batches of the reference loop decoded together by the pipelined loop (transcribe_batches merge=): a pipelined step "
+                         "is `merge` x `batch` clips; 1 = one batch per decode")
     ap.add_argument("--workload", default="clips", choices=["clips", "longform"],
                     help="clips: BASELINE configs[1] (default); longform: configs[4] — long recordings cut into 30 s windows "
                          "(hop 20 s, stride 5 s each side), timestamp mode, windows batched, timestamp-aware stitching")
@@ -127,11 +130,14 @@ def sustained_tflops():
     return None
 
 
-def ncu_traffic_bytes():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r02_decode_attention_stream_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, bench shape)."""
+NCU_TRAFFIC_CSV = {64: "r02_decode_attention_stream_raw.csv", 128: "r02_decode_attention_stream_b128_raw.csv"}
+
+
+def ncu_traffic_bytes(rows=64):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same shape
+    (profiles/r02_decode_attention_stream[_b128]_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum)."""
     import csv
-    p = os.path.join(ROOT, "profiles", "r02_decode_attention_stream_raw.csv")
+    p = os.path.join(ROOT, "profiles", NCU_TRAFFIC_CSV.get(rows, "missing"))
     try:
         rows = list(csv.reader(open(p)))
         hdr, units, data = rows[0], rows[1], rows[2:]
@@ -472,11 +478,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     sh = SHAPES[args.model]
     B, K, W = args.batch, args.steps, args.warmup
+    G = 1 if args.no_pipeline else max(1, args.merge)      # batches per merged decode of the pipelined loop
 
     # random-init weights of the architecture (HF init), built directly on the GPU
     with torch.device(dev):
         hf = build_hf_model(sh, seed=1234)
-    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev), output_layout="5.x")
+    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B * G, device=str(dev), output_layout="5.x")
     hf_cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU baseline is reported at N=1 only
         hf_cpu = hf.to("cpu")
@@ -485,7 +492,7 @@ def main():
 
     # manifest shard of this rank: clip ids [rank*n, (rank+1)*n) mapped onto a pool of distinct synthetic clips
     pool = torch.from_numpy(synth_batch(rank * POOL_CLIPS, POOL_CLIPS)).pin_memory()
-    n_steps_total = W + K
+    n_steps_total = min(W + K, 8)               # distinct host batches (the loops below cycle through them)
 
     def batch_host(i):
         idx = [(i * B + j) % POOL_CLIPS for j in range(B)]
@@ -534,12 +541,18 @@ def main():
     # step (per-launch events cannot ride in the replayed CUDA graph, so this pass launches the kernels directly)
     prof_ms, prof_n, prof_bytes = 0.0, 0, 0.0
     if rank == 0:
+        # at the row count the headline decodes: G merged batches when the pipelined loop merges
+        pcm_prof = torch.cat([dev_batches[i % len(dev_batches)] for i in range(G)]) if G > 1 else None
         model.profile(True)
         for i in range(min(K, 2)):
-            step_device(W + i)
+            if pcm_prof is None:
+                step_device(W + i)
+            else:
+                model.decode(model.encode(log_mel(pcm_prof, None, sh.n_mel)), prompt, args.max_length, False)
         torch.cuda.synchronize()
         prof_ms, prof_n = model.profile(False)
         prof_bytes = getattr(model, "last_profile_bytes", 0.0)
+        del pcm_prof
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -577,7 +590,7 @@ def main():
         barrier()
         e0.record()
         for i in range(K):
-            model.transcribe_pcm(host_batches[W + i], args.max_length, out_tokens=out_tok, out_lengths=out_len)
+            model.transcribe_pcm(host_batches[(W + i) % len(host_batches)], args.max_length, out_tokens=out_tok, out_lengths=out_len)
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -593,23 +606,24 @@ def main():
     # run on a small SM partition while batch i decodes on the rest (model.transcribe_batches).  Steady state: the pipeline is
     # primed by the warm-up batches; the timed region holds exactly K stage-1 passes (batches W+1 .. W+K) and K decodes
     # (batches W .. W+K-1) and ends with a device synchronise, so the last stage-1 pass is inside it.
-    seq = {"value": value, "ms_per_step": ms_max / K, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    seq = {"value": value, "ms_per_step": ms_max / K, "clips_per_step": B, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     pipeline = None
     if not args.no_pipeline:
         try:
-            sms = model.enable_pipeline(args.pipeline_sms)
+            sms = model.enable_pipeline(args.pipeline_sms if args.pipeline_sms > 0 else (16 if G == 1 else 24))
         except (NotImplementedError, RuntimeError) as ex:
             sms = None
             pipeline = {"unavailable": f"{type(ex).__name__}: {ex}"}
         if sms:
             def timed_pipeline(batches_fn):
-                gen = model.transcribe_batches((batches_fn(i) for i in range(W + K + 1)), args.max_length)
-                for _ in range(W):
+                # a pipelined step = G batches of B clips: G stage-1 passes and ONE merged decode over G * B rows
+                gen = model.transcribe_batches((batches_fn(i) for i in range((W + K + 1) * G)), args.max_length, merge=G)
+                for _ in range(W * G):
                     next(gen)
                 barrier()
                 l0 = model.ctx.launch_count()
                 e0.record()
-                got = [next(gen) for _ in range(K)]
+                got = [next(gen) for _ in range(K * G)]
                 torch.cuda.synchronize()
                 e1.record()
                 barrier()
@@ -629,27 +643,31 @@ def main():
             if world > 1:       # final result gather (the only collective of the path)
                 from taiwan_whisper_b200.shard import gather_token_rows
                 gather_token_rows(torch.cat([g[0] for g in got]).to(dev), torch.cat([g[1] for g in got]).to(dev),
-                                  model._rules(False)["pad"], world * K * B)
-            value = world * K * B * CLIP_SECONDS / (p_ms / 1000.0)
+                                  model._rules(False)["pad"], world * K * B * G)
+            value = world * K * B * G * CLIP_SECONDS / (p_ms / 1000.0)
             ms_max = p_ms
             launches = p_launches
-            pipeline = {"encoder_sms": sms[0], "decode_sms": sms[1],
-                        "what": "log-mel + encoder + cross-K/V of batch i+1 in a CUDA green context of encoder_sms SMs, concurrent with the "
-                                "greedy decode of batch i on the other decode_sms SMs (model.transcribe_batches -> tw_pipeline_encode / "
-                                "tw_pipeline_decode); device-resident PCM for `value`, pinned host PCM for `e2e`",
+            pipeline = {"encoder_sms": sms[0], "decode_sms": sms[1], "merge": G, "clips_per_step": B * G,
+                        "what": "log-mel + encoder + cross-K/V of the next batches in a CUDA green context of encoder_sms SMs, concurrent with the "
+                                "greedy decode of the current ones on the other decode_sms SMs (model.transcribe_batches -> tw_pipeline_encode_at / "
+                                "tw_pipeline_decode); device-resident PCM for `value`, pinned host PCM for `e2e`"
+                                + (f"; merge = {G}: {G} consecutive {B}-clip batches of the reference loop are encoded one by one into one slot and "
+                                   f"decoded TOGETHER as {B * G} rows (a decode step streams the weights and runs its chain of small kernels once "
+                                   f"whatever the row count), so a pipelined step = {B * G} clips; `sequential` is the strict one-batch-per-call loop"
+                                   if G > 1 else ""),
                         "stage_ms_in_partition": model.last_stage_ms()}
             if not args.no_e2e:
                 pe_ms, _, _ = timed_pipeline(lambda i: host_batches[i % len(host_batches)])
-                e2e = {"value": world * K * B * CLIP_SECONDS / (pe_ms / 1000.0), "unit": "audio-s/s",
-                       "h2d_bytes_per_step": int(host_batches[0].numel() * 2), "d2h_bytes_per_step": int(B * n_gen * 4 + B * 4),
-                       "ms_per_step": pe_ms / K, "api": "B200WhisperForConditionalGeneration.transcribe_batches -> tw_pipeline_encode / tw_pipeline_decode"}
+                e2e = {"value": world * K * B * G * CLIP_SECONDS / (pe_ms / 1000.0), "unit": "audio-s/s",
+                       "h2d_bytes_per_step": int(G * host_batches[0].numel() * 2), "d2h_bytes_per_step": int(G * (B * n_gen * 4 + B * 4)),
+                       "ms_per_step": pe_ms / K, "api": "B200WhisperForConditionalGeneration.transcribe_batches -> tw_pipeline_encode_at / tw_pipeline_decode"}
 
     if rank == 0:
         hbm, tf, which = peaks()
         tf_sus = sustained_tflops()
         if not isinstance(stage, dict):
             stage = {}
-        bytes_per_launch = B * 1500 * 2 * sh.d_model * 2          # K|V rows of one decoder layer for the batch, bf16
+        bytes_per_launch = B * G * 1500 * 2 * sh.d_model * 2      # K|V rows of one decoder layer for the decoded rows, bf16
         if prof_bytes > 0:                                        # split decode: one launch streams one sub-batch
             bytes_per_launch = int(prof_bytes)
         roof = None
@@ -657,8 +675,9 @@ def main():
             ach = bytes_per_launch / (prof_ms / prof_n / 1000.0) / 1e9
             roof = {"kernel": "decode_attention_partial (cross-attention K/V streaming, 1 launch per layer per token)",
                     "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "peak_source": which,
-                    "traffic": ncu_traffic_bytes() if (args.model == MODEL and B == BATCH) else None,
-                    "traffic_source": "profiles/r02_decode_attention_stream.ncu-rep (ncu --set full, same shape)",
+                    "traffic": ncu_traffic_bytes(B * G) if (args.model == MODEL and B == BATCH) else None,
+                    "traffic_source": f"profiles/{NCU_TRAFFIC_CSV.get(B * G, '-')} (ncu --set full, same shape: {B * G} clips per launch)",
+                    "rows": f"{B * G} clips per launch (the row count of the headline's decode)",
                     "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
                     "algorithmic_bytes_per_launch": bytes_per_launch}
         # per-stage roofline of the last e2e step (north_star: every stage against HBM or tensor-core peak)
@@ -689,10 +708,11 @@ def main():
             "metric": "rtfx_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"whisper-{args.model} pseudo-labelling: {B} x 30 s 16 kHz clips per GPU per step, log-mel + "
+            "config": {"workload": f"whisper-{args.model} pseudo-labelling: batches of {B} x 30 s 16 kHz clips per GPU, log-mel + "
                                    f"encoder + cross-K/V + greedy decode, zh/transcribe, max_length {args.max_length} "
-                                   f"({n_gen} generated tokens/clip)",
-                       "batch_per_gpu": B, "max_length": args.max_length, "weights": "random-init (HF init, seed 1234)",
+                                   f"({n_gen} generated tokens/clip); a step = {G} batch(es) = {B * G} clips"
+                                   + (f" (pipelined loop, {G} batches decoded together)" if G > 1 else ""),
+                       "batch_per_gpu": B, "clips_per_step": B * G, "max_length": args.max_length, "weights": "random-init (HF init, seed 1234)",
                        "parallelism": f"manifest sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs larger than L2: each step streams >= 15 GB of K/V and weights (L2 is 126 MB)",
                        "pipeline": pipeline if pipeline is not None else "off (sequential batch loop)",

@@ -161,13 +161,19 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
  *   tw_pipeline_encode   ASYNCHRONOUS stage 1 of a batch into slot 0 / 1: copy of int16 PCM [B, 480000] (host — it must stay valid until
  *                        the matching tw_pipeline_decode returns — or device), log-mel, encoder, cross-K/V.  Waits (on the device)
  *                        for the decode that last used the slot.
- *   tw_pipeline_decode   stage 2 of the batch in `slot`: greedy decode, ids to HOST buffers, synchronised on return
- *                        (arguments as tw_transcribe_host).
+ *   tw_pipeline_encode_at  the same for a batch that becomes clips clip0 .. clip0 + B - 1 of the slot: several batches of the
+ *                        reference's loop are staged one after the other into one slot and decoded TOGETHER by one tw_pipeline_decode
+ *                        call over clip0 + B rows (merged decode).  A decode step streams the decoder weights once whatever the row
+ *                        count, so two 64-clip batches decoded as 128 rows pay the weight / small-kernel chain of every token once
+ *                        instead of twice; the model must have been loaded with max_batch >= the merged row count.
+ *   tw_pipeline_decode   stage 2 of the batch(es) in `slot`: greedy decode of rows 0 .. B - 1, ids to HOST buffers, synchronised on
+ *                        return (arguments as tw_transcribe_host).
  * Use: encode(b0, 0); for i: { encode(b[i+1], (i+1)&1); decode(i&1) -> ids of b[i] }.  Ids equal tw_transcribe_host's up to the
  * bf16 rounding of a different row split of the K|V stream. */
 TW_API int tw_pipeline_enable(tw_model* m, int n_enc_sms);
 TW_API int tw_pipeline_info(const tw_model* m, int* n_enc_sms, int* n_dec_sms);
 TW_API int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot);
+TW_API int tw_pipeline_encode_at(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot, int clip0);
 TW_API int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int P, const tw_rules* rules, int max_length,
                               int32_t* out_tokens_host, int32_t* out_lengths_host);
 

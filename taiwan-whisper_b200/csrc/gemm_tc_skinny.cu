@@ -1,4 +1,4 @@
-// tcgen05 GEMM for the decode steps (M <= 64 rows):  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias), bf16 -> fp32.
+// tcgen05 GEMM for the decode steps (M <= 256 rows, in 64-row blocks):  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias), bf16 -> fp32.
 //
 // At M <= 64 the GEMM is a weight stream and its K loop is paced by how many bytes TMA has in flight: the general
 // kernel (gemm_tc.cu) moves one 64-wide K block per TMA operation and measured ~205 ns per K block whether 8 or 16
@@ -14,6 +14,10 @@
 // Same roles as gemm_tc.cu: warp 0 TMA producer (weights prefetched before griddepcontrol.wait), warp 1 MMA
 // issuer + TMEM owner, warps 2-5 epilogue (bias / GELU / fp32 residual add with split-K atomics / fp32 store /
 // KV-cache scatter of the fused QKV projection).
+// Batches above 64 rows (merged decode of several 64-clip batches) add a row-block index to the tile space instead of
+// widening the instruction: an M = 128 instruction would double the K loop of every CTA (A-row pacing) and bring 128 rows
+// of A per K block; two M = 64 tiles over a column tile of twice the width keep the per-CTA K loop and the tile count of
+// the 64-row case (the second reader of a weight tile is served by L2).
 #include <stdlib.h>
 
 #include <map>
@@ -61,7 +65,8 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;     // warp-uniform role index
     const int tiles_n = (N + BN - 1) / BN;
-    const int num_tiles = tiles_n * ksplit;                     // one M tile
+    const int mblocks = (M + 63) / 64;                          // 64-row blocks of A (row blocks of one column tile are adjacent work items)
+    const int num_tiles = tiles_n * mblocks * ksplit;
     const int k_blocks_total = K / 64;                          // K % 64 == 0 (checked by the launcher)
     const int kb_per_split = (k_blocks_total + ksplit - 1) / ksplit;
 
@@ -94,7 +99,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // weights of the first work item do not depend on the previous kernel: stream them before the dependency wait
         int prefetched = 0;
         if ((int)blockIdx.x < num_tiles) {
-            const int ks = blockIdx.x % ksplit, n_blk = blockIdx.x / ksplit;
+            const int ks = blockIdx.x % ksplit, n_blk = blockIdx.x / (ksplit * mblocks);
             const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
             const int n_stage = (kb1 - kb0 + SK2_KSUB - 1) / SK2_KSUB;
             prefetched = min(Cfg::STAGES, n_stage);
@@ -111,7 +116,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int ks = tile % ksplit, n_blk = tile / ksplit;
+            const int ks = tile % ksplit, m_blk = (tile / ksplit) % mblocks, n_blk = tile / (ksplit * mblocks);
             const int kb0 = ks * kb_per_split, kb1 = min(k_blocks_total, kb0 + kb_per_split);
             // grouped GEMM: this tile's output columns belong to group (n_blk*BN)/group_n, whose A slice starts K columns later per group
             const int a_kb0 = epi.group_n > 0 ? ((n_blk * BN) / epi.group_n) * k_blocks_total : 0;
@@ -120,12 +125,12 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 if (prefetched > 0) {
                     --prefetched;
-                    if (elect_one_sync()) tma_load_3d(&map_a, fb, sa, 0, 0, a_kb0 + kb);
+                    if (elect_one_sync()) tma_load_3d(&map_a, fb, sa, 0, m_blk * 64, a_kb0 + kb);
                 } else {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                     if (elect_one_sync()) {
                         mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-                        tma_load_3d(&map_a, fb, sa, 0, 0, a_kb0 + kb);
+                        tma_load_3d(&map_a, fb, sa, 0, m_blk * 64, a_kb0 + kb);
                         tma_load_3d(&map_w, fb, sa + Cfg::A_REGION, 0, n_blk * BN, kb);
                     }
                 }
@@ -173,15 +178,15 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int quarter = warp & 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int ks = tile % ksplit, n_blk = tile / ksplit;
+            const int ks = tile % ksplit, m_blk = (tile / ksplit) % mblocks, n_blk = tile / (ksplit * mblocks);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
             tc_fence_after();
-            const int row = quarter * 16 + (lane & 15);          // M = 64 accumulator: 16 rows per TMEM lane quarter
+            const int row = m_blk * 64 + quarter * 16 + (lane & 15);     // M = 64 accumulator: 16 rows per TMEM lane quarter
             const bool row_ok = lane < 16 && row < M;
             const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            if (quarter * 16 < M) {                     // warp-uniform: quarters beyond M have nothing to store
+            if (m_blk * 64 + quarter * 16 < M) {        // warp-uniform: quarters beyond M have nothing to store
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
                     const int n0 = n_blk * BN + c0;
@@ -310,7 +315,8 @@ static int sk2_map(tw_ctx* ctx, const void* ptr, int64_t rows, int64_t K, int64_
 }
 
 bool gemm_tc_skinny_supported(int M, int N, int K, const GemmEpi& epi) {
-    return !g_sk2_broken && M >= 1 && M <= 64 && (K % 64) == 0 && K >= 64 && N >= 8 && epi.mode != EPI_GELU_POS;
+    return !g_sk2_broken && M >= 1 && M <= 256 && (M <= 64 || epi.group_n == 0) && (K % 64) == 0 && K >= 64 && N >= 8 &&
+           epi.mode != EPI_GELU_POS;
 }
 
 int gemm_tc_skinny_init(tw_ctx* ctx) {
@@ -348,14 +354,27 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
         ctx->set_error(TW_E_UNSUPPORTED, "gemm_tc_skinny: unsupported shape / alignment");
         return TW_E_UNSUPPORTED;
     }
-    // 64-wide tiles once 32-wide ones would need more than `waves` passes over the SMs (tuning knob TWB200_SK_WAVES; 1 = measured default: 2, i.e. fc1 as 160 32-wide
-    // tiles on 148 CTAs instead of 80 64-wide ones, is 12 ms per decode slower)
-    static const int waves = getenv("TWB200_SK_WAVES") ? atoi(getenv("TWB200_SK_WAVES")) : 1;
-    int BN = (ceil_div(N, 32) > waves * ctx->sm_count) ? 64 : 32;
-    // the K loop of a tile costs the same for 32, 64 or 128 columns (A-operand pacing, see the header): very wide outputs (vocab
-    // head) take 128-wide tiles once 64-wide ones would need more than two passes over the SMs
-    static const int wide = getenv("TWB200_SK_WIDE") ? atoi(getenv("TWB200_SK_WIDE")) : 1;
-    if (wide && BN == 64 && ceil_div(N, 64) > 2 * ctx->sm_count) BN = 128;
+    // Column-tile width: the K loop of a tile costs the same for 32, 64 or 128 columns (A-operand pacing, see the header), so the
+    // narrowest width whose tile count (column tiles x 64-row blocks) fits one pass over the SMs streams the matrix with the most
+    // CTAs (fc1 as 160 32-wide tiles on 148 CTAs instead of 80 64-wide ones is 12 ms per decode slower); very wide outputs
+    // (vocabulary head) take 128-wide tiles.  The residual epilogue splits K (fp32 atomics) only as far as idle SMs remain: a
+    // cost model that traded wider tiles for deeper splits (more CTAs, shorter K loops) measured 3-5 % SLOWER per decoder layer
+    // at 64 and 128 rows — the extra atomic traffic on the residual stream costs more than the shorter loops save
+    // (profiles/r02_merged_decode.md).  TWB200_SK_BN forces a width.
+    static const int force_bn = getenv("TWB200_SK_BN") ? atoi(getenv("TWB200_SK_BN")) : 0;
+    const int mblocks = ceil_div(M, 64);
+    const int kstages = ceil_div(K / 64, SK2_KSUB);
+    auto split_for = [&](int bn) {
+        if (epi.mode != EPI_RESID) return 1;
+        int ks = ctx->sm_count / (ceil_div(N, bn) * mblocks);
+        if (ks > kstages) ks = kstages;
+        if (ks < 1) ks = 1;
+        return ceil_div(kstages, ceil_div(kstages, ks));      // whole stages of KSUB blocks per split
+    };
+    int BN = 32;
+    if (ceil_div(N, 32) * mblocks > ctx->sm_count) BN = 64;
+    if (BN == 64 && ceil_div(N, 64) * mblocks > (mblocks > 1 ? 1 : 2) * ctx->sm_count) BN = 128;
+    if (force_bn == 32 || force_bn == 64 || force_bn == 128) BN = force_bn;
     int n_groups = 1;
     if (epi.group_n > 0) {
         if (epi.group_n % 32 || N % epi.group_n || epi.mode == EPI_RESID) {
@@ -368,16 +387,8 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     CUtensorMap ma, mw;
     TW_CHECK(sk2_map(ctx, A, M, (int64_t)K * n_groups, lda, 64, &ma));
     TW_CHECK(sk2_map(ctx, W, N, K, ldw, BN, &mw));
-    int tiles = ceil_div(N, BN);
-    int ksplit = 1;
-    if (epi.mode == EPI_RESID) {            // split K (in whole stages of KSUB blocks) so that ~one wave of CTAs streams the matrix
-        const int kstages = ceil_div(K / 64, SK2_KSUB);
-        ksplit = ctx->sm_count / tiles;
-        if (ksplit > kstages) ksplit = kstages;
-        if (ksplit < 1) ksplit = 1;
-        const int per = ceil_div(kstages, ksplit);
-        ksplit = ceil_div(kstages, per);
-    }
+    int tiles = ceil_div(N, BN) * mblocks;
+    const int ksplit = split_for(BN);
     tiles *= ksplit;
     const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
     // the kernel splits K in units of K blocks: make kb_per_split a multiple of KSUB by construction

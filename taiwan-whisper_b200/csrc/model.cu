@@ -167,6 +167,8 @@ struct tw_model {
     // debug timeline (TWB200_TRACE=<position>): CUDA events after every kernel of two middle decoder layers at that
     // position (non-graph path only), printed to stderr at the end of the decode call
     int trace_pos = -1;
+    int skip_mask = 0;           // TWB200_SKIP (timing experiments only, results are garbage): kernels left out of the decode step —
+                                 // 1 LayerNorms, 2 self-attention, 4 cross-attention stream, 8 QKV, 16 self out-proj, 32 cross q, 64 cross out-proj, 128 fc1, 256 fc2
     std::vector<std::pair<cudaEvent_t, std::string>> trace;
     // in-situ timing of the dominant kernel (cross-attention K/V streaming) for bench.py's roofline
     bool prof_on = false;
@@ -499,11 +501,12 @@ int encode_impl(tw_model* m, const float* mel, int B, void* enc_out, int tap_lay
 }
 
 template <typename T>
-int cross_kv_impl(tw_model* m, const void* enc_out, int B, cudaStream_t st) {
+int cross_kv_impl(tw_model* m, const void* enc_out, int B, cudaStream_t st, int clip0 = 0) {
     const tw_model_desc& D = m->desc;
     const int d = D.d_model, M = B * TW_N_CTX;
     for (int l = 0; l < D.dec_layers; ++l) {
-        T* dst = (T*)m->xkv + (size_t)l * D.max_batch * TW_N_CTX * 2 * d;
+        // rows of clips clip0 .. clip0 + B - 1 of the layer's store (clip0 > 0: a later part of a merged decode batch)
+        T* dst = (T*)m->xkv + ((size_t)l * D.max_batch + clip0) * TW_N_CTX * 2 * d;
         TW_CHECK(gemm<T>(m, (const T*)enc_out, d, (const T*)m->dec[l].cross.kv_w, d, M, 2 * d, d,
                          mk_epi(EPI_STORE, m->dec[l].cross.kv_b, dst, 2 * d), st));
     }
@@ -654,10 +657,11 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
     g_pdl = pdl_on;
     mark(-1, "embed");
     const int32_t* pt = m->d_page_table;
+    const int skip = m->skip_mask;
     for (int l = 0; l < D.dec_layers; ++l) {
         const LayerW& L = m->dec[l];
         T* cache = (T*)m->self_kv + l * self_layer;                       // the layer's page pool
-        layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
+        if (!(skip & 1)) layernorm<T>(x, L.ln1_g, L.ln1_b, xn, B, d, st);
         mark(l, "ln1");
         GemmEpi qe = mk_epi(EPI_STORE, L.self.qkv_b, qkv, 3 * d);
         // the K|V columns of the fused QKV projection land in the cache row of this position — only the skinny tcgen05
@@ -672,16 +676,16 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
             qe.page_table = pt;
             qe.pt_stride = m->kv_pages;
         }
-        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
+        if (!(skip & 8)) TW_CHECK(gemm<T>(m, xn, d, (const T*)L.self.qkv_w, d, B, 3 * d, d, qe, st));
         mark(l, "qkv");
         if (!fused_append) { kv_append<T>(qkv, cache, m->d_step, B, d, D.max_target, st, pt, m->kv_pages); ctx->launches += 1; }
-        self_attention_decode<T>(qkv, 3 * d, cache, 0, 0, d_pos, B, H, att, st, pt, m->kv_pages, S.finished);
+        if (!(skip & 2)) self_attention_decode<T>(qkv, 3 * d, cache, 0, 0, d_pos, B, H, att, st, pt, m->kv_pages, S.finished);
         mark(l, "self_attn");
-        TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
+        if (!(skip & 16)) TW_CHECK(gemm<T>(m, att, d, (const T*)L.self.o_w, d, B, d, d, mk_epi(EPI_RESID, L.self.o_b, x, d), st));
         mark(l, "self_o");
-        layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
+        if (!(skip & 1)) layernorm<T>(x, L.ln2_g, L.ln2_b, xn, B, d, st);
         mark(l, "ln2");
-        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
+        if (!(skip & 32)) TW_CHECK(gemm<T>(m, xn, d, (const T*)L.cross.q_w, d, B, d, d, mk_epi(EPI_STORE, L.cross.q_b, q, d), st));
         mark(l, "cross_q");
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (m->prof_on && l == D.dec_layers / 2 && m->prof_used + 2 <= (int)m->prof_ev.size()) {
@@ -690,20 +694,21 @@ int launch_step(tw_model* m, int B, const RulesDev& R, const DecodeState& S, con
             m->prof_used += 2;
             m->prof_bytes = (double)B * TW_N_CTX * (m->absorb_now ? 1 : 2) * d * sizeof(T);
         }
-        if (m->absorb_now) {
+        if (skip & 4) {
+        } else if (m->absorb_now) {
             TW_CHECK(cross_absorbed<T>(m, L, q, att, B, l, st, e0, e1, S));
         } else {
             decode_attention<T>(q, d, (const T*)m->xkv + l * cross_layer, (int64_t)TW_N_CTX * 2 * d, TW_N_CTX, nullptr, B, H, m->dpartial, att,
                                 st, e0, e1, S.active, S.n_active);
         }
         mark(l, "cross_attn+combine");
-        TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
+        if (!(skip & 64)) TW_CHECK(gemm<T>(m, att, d, (const T*)L.cross.o_w, d, B, d, d, mk_epi(EPI_RESID, L.cross.o_b, x, d), st));
         mark(l, "cross_o");
-        layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
+        if (!(skip & 1)) layernorm<T>(x, L.ln3_g, L.ln3_b, xn, B, d, st);
         mark(l, "ln3");
-        TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
+        if (!(skip & 128)) TW_CHECK(gemm<T>(m, xn, d, (const T*)L.fc1_w, d, B, D.ffn, d, mk_epi(EPI_GELU, L.fc1_b, hmid, D.ffn), st));
         mark(l, "fc1");
-        TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
+        if (!(skip & 256)) TW_CHECK(gemm<T>(m, hmid, D.ffn, (const T*)L.fc2_w, D.ffn, B, d, D.ffn, mk_epi(EPI_RESID, L.fc2_b, x, d), st));
         mark(l, "fc2");
         ctx->launches += 6;       // 3 LN, self-attention, cross-attention stream + combine; the GEMMs count themselves
     }
@@ -763,7 +768,8 @@ int decode_impl(tw_model* m, int B, const int32_t* prompt, int P, const RulesDev
     StepIo io{out_tokens, out_lengths, forced, logits_tap};
     if (want_graph) io = StepIo{m->d_out_tok, m->d_out_len, nullptr, nullptr};
     if (want_graph) TW_CUDA_OK(ctx, cudaMemsetAsync(m->d_out_len, 0, B * sizeof(int32_t), st));
-    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, m->row_budget_on ? 1 : 0,
+    m->skip_mask = getenv("TWB200_SKIP") ? atoi(getenv("TWB200_SKIP")) : 0;      // re-read per call: one process can sweep masks
+    GraphKey key{B, R.eos, R.pad, R.ts_begin, R.no_timestamps, R.max_initial_ts, (m->row_budget_on ? 1 : 0) | (m->skip_mask << 1),
                  m->absorb_now ? m->cur_enc : nullptr, m->xkv, ctx->sm_count};
     cudaGraphExec_t exec = nullptr;
     uint64_t exec_kernels = 0;
@@ -957,6 +963,7 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     m->use_pdl = !(gp && strcmp(gp, "0") == 0);
     const char* gtr = getenv("TWB200_TRACE");
     m->trace_pos = gtr ? atoi(gtr) : -1;
+    m->skip_mask = getenv("TWB200_SKIP") ? atoi(getenv("TWB200_SKIP")) : 0;
     m->absorb_ok = (D.dtype == TW_BF16) && absorbed_attention_supported(D.heads, D.d_model);
     WeightTable wt;
     for (size_t i = 0; i < n; ++i)
@@ -1258,12 +1265,20 @@ int tw_pipeline_info(const tw_model* m, int* n_enc_sms, int* n_dec_sms) {
 }
 
 int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot) {
+    return tw_pipeline_encode_at(m, pcm, n_valid_host, B, slot, 0);
+}
+
+int tw_pipeline_encode_at(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot, int clip0) {
     if (!check_model(m, "tw_pipeline_encode")) return TW_E_INVALID;
     tw_ctx* ctx = m->ctx;
     auto& P = m->pipe;
-    if (!P.on || slot < 0 || slot > 1 || B <= 0 || B > m->desc.max_batch || !pcm) {
-        ctx->set_error(TW_E_INVALID, "tw_pipeline_encode: pipeline not enabled, bad slot (0 / 1), bad batch or null buffer");
+    if (!P.on || slot < 0 || slot > 1 || B <= 0 || clip0 < 0 || clip0 + B > m->desc.max_batch || !pcm) {
+        ctx->set_error(TW_E_INVALID, "tw_pipeline_encode: pipeline not enabled, bad slot (0 / 1), bad batch / clip offset or null buffer");
         return TW_E_INVALID;
+    }
+    if (clip0 > 0 && use_absorb(m, 1)) {      // (the first part would have skipped its K|V projection)
+        ctx->set_error(TW_E_UNSUPPORTED, "tw_pipeline_encode_at: merged decode batches are not available on the absorbed cross-attention path");
+        return TW_E_UNSUPPORTED;
     }
     const tw_model_desc& D = m->desc;
     cudaStream_t st = P.s_enc;
@@ -1286,12 +1301,13 @@ int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_h
         const float* clip_max = nullptr;
         if ((r = logmel_run(ctx, m->ws_pcm, TW_I16, TW_N_SAMPLES, nv, B, D.n_mel, m->ws_mel, st, false, &clip_max)) != TW_OK) break;
         cudaEventRecord(m->ev[1], st);
-        r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, P.enc_out[slot], -1, nullptr, st, clip_max)
-                               : encode_impl<float>(m, m->ws_mel, B, P.enc_out[slot], -1, nullptr, st, clip_max);
+        void* const enc_part = (char*)P.enc_out[slot] + (size_t)clip0 * TW_N_CTX * D.d_model * m->esz;
+        r = D.dtype == TW_BF16 ? encode_impl<__nv_bfloat16>(m, m->ws_mel, B, enc_part, -1, nullptr, st, clip_max)
+                               : encode_impl<float>(m, m->ws_mel, B, enc_part, -1, nullptr, st, clip_max);
         if (r != TW_OK) break;
         cudaEventRecord(m->ev[2], st);
         if (!use_absorb(m, B))
-            r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, P.enc_out[slot], B, st) : cross_kv_impl<float>(m, P.enc_out[slot], B, st);
+            r = D.dtype == TW_BF16 ? cross_kv_impl<__nv_bfloat16>(m, enc_part, B, st, clip0) : cross_kv_impl<float>(m, enc_part, B, st, clip0);
         if (r != TW_OK) break;
         cudaEventRecord(m->ev[3], st);
         if (cudaEventRecord(P.enc_done[slot], st) != cudaSuccess) { r = TW_E_CUDA; break; }

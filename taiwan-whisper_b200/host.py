@@ -621,13 +621,23 @@ class B200WhisperForConditionalGeneration:
         self.pipeline_sms = (a.value, b.value)
         return self.pipeline_sms
 
-    def transcribe_batches(self, batches, max_length: int, return_timestamps: bool = False, language="zh", task="transcribe"):
+    def transcribe_batches(self, batches, max_length: int, return_timestamps: bool = False, language="zh", task="transcribe",
+                           merge: int = 1):
         """The reference's batch loop (ref training/run_pseudo_labelling.py:915-918) as a generator: yields (tokens, lengths) — pinned
-        host int32 tensors [B, max_length - P] / [B], a fresh pair per batch — for every int16 PCM batch [B, 480000] of `batches`
-        (pinned host or device tensors), in order.  While batch i decodes, batch i+1 is already in its log-mel / encoder /
-        cross-K/V stage on the other SM partition (`enable_pipeline` first)."""
+        host int32 tensors [B, max_length - P] / [B] — for every int16 PCM batch [B, 480000] of `batches` (pinned host or device
+        tensors), in order.  While batch i decodes, batch i+1 is already in its log-mel / encoder / cross-K/V stage on the other SM
+        partition (`enable_pipeline` first).
+
+        `merge` > 1 decodes that many consecutive batches TOGETHER (tw_pipeline_encode_at): each is encoded on its own — the
+        encoder is compute-bound, its cost follows the clip count — into consecutive rows of one slot, and one greedy decode runs
+        over all rows.  A decode step streams the decoder weights and runs its chain of small dependent kernels once whatever
+        the row count, so merged batches pay them once; per row nothing changes (same kernels, same arithmetic per row: ids equal
+        the unmerged loop's up to the bf16 rounding of a different K|V row split).  The model needs max_batch >= the merged rows;
+        results are still yielded per input batch."""
         if not getattr(self, "pipeline_sms", None):
             raise RuntimeError("transcribe_batches needs enable_pipeline() first")
+        if merge < 1:
+            raise ValueError("merge must be >= 1")
         prompt = self._init_tokens(language, task, return_timestamps)
         n_gen = max_length - len(prompt)
         if n_gen <= 0 or max_length > self.shape.max_target:
@@ -637,33 +647,43 @@ class B200WhisperForConditionalGeneration:
                                       r["no_timestamps"], r["max_initial_ts"])
         p = (C.c_int32 * len(prompt))(*prompt)
         lib, h = self.ctx.lib, C.c_void_p(self.handle)
+        it = iter(batches)
 
-        def encode(pcm, slot):
-            if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != N_SAMPLES or pcm.shape[0] > self.max_batch:
-                raise ValueError("transcribe_batches expects int16 tensors [B <= max_batch, 480000]")
-            pcm = pcm.contiguous()
-            self.ctx.check(lib.tw_pipeline_encode(h, pcm.data_ptr(), None, pcm.shape[0], slot))
-            return pcm                               # kept alive until its decode has returned
+        def encode_group(slot):
+            """Stage 1 of the next `merge` batches (fewer at the end of the loop, or when the next batch would not fit max_batch)
+            into `slot`; returns the row count of each and keeps the PCM tensors alive until their decode has returned."""
+            sizes, alive = [], []
+            while len(sizes) < merge:
+                pcm = self._pending if self._pending is not None else next(it, None)
+                self._pending = None
+                if pcm is None:
+                    break
+                if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != N_SAMPLES or pcm.shape[0] > self.max_batch or pcm.shape[0] == 0:
+                    raise ValueError("transcribe_batches expects int16 tensors [1 <= B <= max_batch, 480000]")
+                if sum(sizes) + pcm.shape[0] > self.max_batch:
+                    self._pending = pcm                # opens the next group
+                    break
+                pcm = pcm.contiguous()
+                self.ctx.check(lib.tw_pipeline_encode_at(h, pcm.data_ptr(), None, pcm.shape[0], slot, sum(sizes)))
+                sizes.append(pcm.shape[0])
+                alive.append(pcm)
+            return (sizes, alive) if sizes else None
 
+        self._pending = None
         with torch.cuda.device(self.device):
-            it = iter(batches)
-            try:
-                cur = encode(next(it), 0)
-            except StopIteration:
-                return
+            cur = encode_group(0)
             i = 0
             while cur is not None:
-                nxt = None
-                try:
-                    nxt = encode(next(it), (i + 1) & 1)
-                except StopIteration:
-                    pass
-                B = cur.shape[0]
+                nxt = encode_group((i + 1) & 1)
+                B = sum(cur[0])
                 out_tokens = torch.empty((B, n_gen), dtype=torch.int32).pin_memory()
                 out_lengths = torch.empty((B,), dtype=torch.int32).pin_memory()
                 self.ctx.check(lib.tw_pipeline_decode(h, i & 1, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
                                                       out_lengths.data_ptr()))
-                yield out_tokens, out_lengths
+                b0 = 0
+                for n in cur[0]:
+                    yield out_tokens[b0:b0 + n], out_lengths[b0:b0 + n]
+                    b0 += n
                 cur = nxt
                 i += 1
         del keep

@@ -126,10 +126,12 @@ def test_gemm_tcgen05_vs_torch(M, N, K, mode):
 
 
 @pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (64, 3840, 1280), (3, 5120, 1280), (64, 1280, 5120), (1, 51866, 1280),
-                                   (5, 384, 384), (64, 128, 128), (2, 384, 1536), (64, 51865, 384), (7, 1152, 384)])
+                                   (5, 384, 384), (64, 128, 128), (2, 384, 1536), (64, 51865, 384), (7, 1152, 384),
+                                   (128, 3840, 1280), (128, 1280, 5120), (128, 5120, 1280), (70, 1280, 1280), (65, 1152, 384),
+                                   (130, 384, 1536), (192, 3840, 1280), (256, 1280, 5120), (200, 51866, 384)])
 @pytest.mark.parametrize("mode", [0, 1, 2, 4])
 def test_gemm_skinny_vs_torch(M, N, K, mode):
-    """tcgen05 skinny GEMM of the decode steps (M <= 64)."""
+    """tcgen05 skinny GEMM of the decode steps (M <= 64 per row block; merged decode batches run 2-4 row blocks)."""
     _cuda()
     from tests.gpu_common import gemm_debug
     impl = 3
@@ -678,6 +680,21 @@ def test_pipelined_batch_loop_matches_sequential(dtype_name):
                 assert toks[j, :4].tolist() == st[j, :4].tolist() and agree >= 0.5, (o, j, agree)
     ms = m.last_stage_ms()
     assert ms["encoder"] > 0 and ms["decode"] > 0
+    # merged decode: groups of 2 / 3 batches decoded as one batch (max_batch 4: [3] | [3] ... cannot merge, so use 2-clip batches)
+    small = [[0, 1], [2, 0], [1, 2], [0, 2], [1]]
+    sb = [host[o].pin_memory() if i % 2 else host[o].cuda() for i, o in enumerate(small)]
+    sseq = [tuple(x.clone() for x in m.transcribe_pcm(host[o].pin_memory(), max_length)) for o in small]
+    for merge in (2, 3):
+        got = list(m.transcribe_batches(sb, max_length, merge=merge))
+        assert len(got) == len(small)
+        for o, (toks, lens), (st, sl) in zip(small, got, sseq):
+            assert toks.shape == (len(o), n) and lens.tolist() == sl.tolist()
+            for j, b in enumerate(o):
+                if dtype_name == "f32":
+                    assert toks[j].tolist() == ora[b]["tokens"][:n], (merge, o, j)
+                else:
+                    agree = (toks[j] == st[j]).float().mean().item()
+                    assert toks[j, :4].tolist() == st[j, :4].tolist() and agree >= 0.5, (merge, o, j, agree)
     # the one-call path still works on the whole GPU afterwards
     t2, _ = m.transcribe_pcm(host[orders[0]].pin_memory(), max_length)
     assert t2.tolist() == seq[0][0].tolist()

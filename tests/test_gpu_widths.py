@@ -132,9 +132,10 @@ def test_benched_width_bf16_vs_hf_bf16(shape_name, B, max_length, timestamps, ro
     assert ours_dis <= hf_dis + max(4, hf_dis // 2), (ours_dis, hf_dis, total)
 
 
-@pytest.mark.parametrize("B,dtype_name", [(70, "f32"), (130, "f32"), (130, "bf16")])
+@pytest.mark.parametrize("B,dtype_name", [(70, "f32"), (130, "f32"), (70, "bf16"), (130, "bf16"), (260, "bf16")])
 def test_decode_batches_beyond_64(B, dtype_name):
-    """B > 64 leaves the skinny GEMM (and its fused cache append): the K|V rows must still reach the paged cache
+    """B > 64: the skinny GEMM runs 2-4 row blocks (fused cache append through the page table for every row block) up to 256
+    rows and the general GEMM with a separate append kernel beyond: the K|V rows must reach the paged cache either way
     (the BN=256 tile ignored the column split).  tiny, distinct clips, sampled rows vs the oracle."""
     _cuda()
     from taiwan_whisper_b200.host import log_mel
