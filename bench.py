@@ -688,7 +688,11 @@ def main():
                     "traffic_source": f"profiles/{NCU_TRAFFIC_CSV.get(B * G, '-')} (ncu --set full, same shape: {B * G} clips per launch)",
                     "rows": f"{B * G} clips per launch (the row count of the headline's decode)",
                     "launches_timed": prof_n, "avg_launch_us": 1000.0 * prof_ms / prof_n,
-                    "algorithmic_bytes_per_launch": bytes_per_launch}
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "how": "CUDA events around one launch per decode step (middle decoder layer) on the launching stream, in a separate pass "
+                           "of the same steps with plain launches (events cannot ride in the replayed CUDA graph)",
+                    "peak_note": "MEASURED_PEAKS.json hbm_gbs is a COPY bandwidth (read + write); this kernel only reads, and a read-only "
+                                 "stream runs up to ~2 % above it (frac may slightly exceed 1)"}
         # per-stage roofline of the last e2e step (north_star: every stage against HBM or tensor-core peak)
         d, ffn, L_e, L_d, V = sh.d_model, sh.ffn, sh.enc_layers, sh.dec_layers, sh.vocab
         enc_flops = B * (2 * 3000 * d * sh.n_mel * 3 + 2 * 1500 * d * d * 3 +

@@ -1,5 +1,5 @@
-"""Short decode run at large-v3 width (d=1280, ffn=5120, 20 heads, vocab 51866, batch 64) with only 1 encoder and
-2 decoder layers, for an ncu launch list of the decode-step kernels (TWB200_GRAPH=0 so every launch is visible)."""
+"""Short decode run at large-v3 width (d=1280, ffn=5120, 20 heads, vocab 51866, batch 64 — or argv 2 rows, e.g. 192 = three
+merged batches) with only 1 encoder and 2 decoder layers, for an ncu launch list of the decode-step kernels (TWB200_GRAPH=0 so every launch is visible)."""
 import os
 import sys
 
@@ -15,8 +15,9 @@ from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa
 sh = WhisperShape("lv3-2dec", 128, 1280, 5120, 20, 1, 2, 51866)
 with torch.device("cuda"):
     hf = build_hf_model(sh, seed=1)
-m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=64)
-enc = (torch.randn((64, 1500, 1280), device="cuda") * 0.5).bfloat16()
+ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=ROWS)
+enc = (torch.randn((ROWS, 1500, 1280), device="cuda") * 0.5).bfloat16()
 prompt = m._init_tokens("zh", "transcribe", False)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 toks, lens = m.decode(enc, prompt, len(prompt) + n, False)
