@@ -646,6 +646,146 @@ self_attention_decode_kernel(const T* __restrict__ q, int64_t q_stride, const T*
     }
 }
 
+// ---- ring variant: the same row order and arithmetic (bit-identical output), but K|V rows land in a per-warp shared-memory ring
+// of SA_RING rows through 16-byte cp.async copies issued SA_RING rows ahead, so every warp keeps SA_RING rows (1 KB each for the
+// CTA's 4 heads in bf16) in flight ALL the time.  The register version above has 4 rows in flight per warp only while it waits
+// and none while it consumes (measured ~3.5 TB/s marginal on the cache at 192 merged rows, where this kernel is ~12 % of a decode
+// step); the ring holds 8.  Each lane reads back exactly the bytes it copied itself: no cross-lane hand-over, no barrier — only
+// cp.async.wait_group.  Every iteration commits one group (an empty one when the warp has run out of rows), so "all but the
+// newest SA_RING - 1 groups complete" always means "the oldest row in the ring has arrived".
+constexpr int SA_RING = 8;
+
+__device__ __forceinline__ void sa_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sa_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sa_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 3 : 1)
+self_attention_decode_ring_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ kv, int64_t kv_clip_stride, int Tk,
+                                  const int32_t* __restrict__ d_tk, int H, T* __restrict__ out, const int32_t* __restrict__ page_table,
+                                  int pt_stride, const int32_t* __restrict__ finished, int early) {
+    constexpr int SEG = 8 * (int)sizeof(T);            // bytes of K (and of V) one lane owns per row
+    extern __shared__ __align__(16) unsigned char sa_ring[];      // [warp][slot][K|V][lane][SEG]
+    __shared__ float s_rec[SA_WARPS][SA_HG][HD + 2];
+    __shared__ int32_t s_pt[SA_MAX_PAGES];
+    pdl_trigger();
+    const int hg = blockIdx.x, b = blockIdx.y;
+    if (finished && finished[b]) { pdl_wait(); return; }
+    const bool pt_smem = page_table && pt_stride <= SA_MAX_PAGES;
+    if (pt_smem && (int)threadIdx.x < pt_stride) s_pt[threadIdx.x] = page_table[(int64_t)b * pt_stride + threadIdx.x];
+    if (!early) pdl_wait();
+    if (pt_smem) __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d_tk) Tk = *d_tk + 1;
+    const int d = H * HD;
+    const int col = hg * SA_HG * HD + lane * 8;
+    const bool active = col < d;
+    const T* kvb = kv + (page_table ? 0 : (int64_t)b * kv_clip_stride) + (active ? col : 0);
+    const int32_t* ptb = page_table ? (pt_smem ? s_pt : page_table + (int64_t)b * pt_stride) : nullptr;
+    auto row_ptr = [&](int r) -> const T* {
+        const int64_t pr = ptb ? (int64_t)ptb[r / TW_KV_PAGE] * TW_KV_PAGE + r % TW_KV_PAGE : (int64_t)r;
+        return kvb + pr * 2 * d;
+    };
+    unsigned char* my = sa_ring + ((size_t)warp * SA_RING * 2 * 32 + lane) * SEG;       // + (slot * 2 + kv) * 32 * SEG
+    auto issue = [&](int i) {              // i-th row of this warp (row warp + i * SA_WARPS) into slot i % SA_RING; one group
+        if (active) {
+            const T* rp = row_ptr(warp + i * SA_WARPS);
+            unsigned char* dst = my + (size_t)((i % SA_RING) * 2) * 32 * SEG;
+#pragma unroll
+            for (int o = 0; o < SEG; o += 16) {
+                sa_cp_async16(dst + o, reinterpret_cast<const unsigned char*>(rp) + o);
+                sa_cp_async16(dst + 32 * SEG + o, reinterpret_cast<const unsigned char*>(rp + d) + o);
+            }
+        }
+        sa_cp_commit();
+    };
+    float qf[8], of[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qf[e] = 0.0f; of[e] = 0.0f; }
+    float mrun = -INFINITY, lrun = 0.0f;
+    const int n_old = early ? Tk - 1 : Tk;                                     // rows [0, n_old) may be read before the wait
+    const int n_mine = Tk > warp ? (Tk - warp + SA_WARPS - 1) / SA_WARPS : 0;     // rows of this warp
+    const int n_old_mine = n_old > warp ? (n_old - warp + SA_WARPS - 1) / SA_WARPS : 0;
+    int issued = 0;
+    for (; issued < SA_RING && issued < n_old_mine; ++issued) issue(issued);
+    if (early) {
+        // rows beyond the ring: one 128-byte line per lane into L2 (lanes 0-3 the K part of this CTA's 4 heads, lanes 4-7 the V part)
+        if (lane < 8 && hg * SA_HG * HD + (lane & 3) * 64 < d) {
+            for (int r = warp + SA_RING * SA_WARPS; r < n_old; r += SA_WARPS) {
+                const int64_t pr = ptb ? (int64_t)ptb[r / TW_KV_PAGE] * TW_KV_PAGE + r % TW_KV_PAGE : (int64_t)r;
+                const T* lp = kv + (page_table ? 0 : (int64_t)b * kv_clip_stride) + pr * 2 * d + (lane >> 2) * d + hg * SA_HG * HD + (lane & 3) * 64;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(lp));
+            }
+        }
+        pdl_wait();
+    }
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[e] = to_f32(q[(int64_t)b * q_stride + col + e]);
+    }
+    // top the ring up to SA_RING groups (the newest row may be issued now; empty groups once the warp has no more rows)
+    for (int g = issued; g < SA_RING; ++g) {
+        if (issued < n_mine) issue(issued++);
+        else sa_cp_commit();
+    }
+    for (int c = 0; c < n_mine; ++c) {
+        sa_cp_wait<SA_RING - 1>();
+        const unsigned char* src = my + (size_t)((c % SA_RING) * 2) * 32 * SEG;
+        float kf[8], vf[8];
+        if (active) {
+            typename Ld8<T>::Raw kraw = Ld8<T>::load(reinterpret_cast<const T*>(src));
+            typename Ld8<T>::Raw vraw = Ld8<T>::load(reinterpret_cast<const T*>(src + 32 * SEG));
+            Ld8<T>::unpack(kraw, kf);
+            Ld8<T>::unpack(vraw, vf);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { kf[e] = 0.0f; vf[e] = 0.0f; }
+        }
+        float dot = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot = fmaf(qf[e], kf[e], dot);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        const float m_new = fmaxf(mrun, dot);
+        const float sc = __expf(mrun - m_new);
+        const float p = __expf(dot - m_new);
+        lrun = lrun * sc + p;
+        mrun = m_new;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) of[e] = fmaf(p, vf[e], of[e] * sc);
+        if (issued < n_mine) issue(issued++);          // into the slot just consumed
+        else sa_cp_commit();
+    }
+    sa_cp_wait<0>();
+    {
+        float* rec = s_rec[warp][lane >> 3];
+        if ((lane & 7) == 0) { rec[0] = mrun; rec[1] = lrun; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rec[2 + (lane & 7) * 8 + e] = of[e];
+    }
+    __syncthreads();
+    {
+        const int hh = threadIdx.x >> 6, e = threadIdx.x & 63;
+        const int h = hg * SA_HG + hh;
+        if (h < H) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < SA_WARPS; ++w) m = fmaxf(m, s_rec[w][hh][0]);
+            float l = 0.0f, o = 0.0f;
+#pragma unroll
+            for (int w = 0; w < SA_WARPS; ++w) {
+                const float sc = (s_rec[w][hh][0] == -INFINITY) ? 0.0f : __expf(s_rec[w][hh][0] - m);
+                l += s_rec[w][hh][1] * sc;
+                o += s_rec[w][hh][2 + e] * sc;
+            }
+            out[(int64_t)b * d + h * HD + e] = from_f32<T>(o / l);
+        }
+    }
+}
+
 template <typename T>
 void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv_clip_stride, int Tk, const int32_t* d_tk, int B, int H,
                            T* out, cudaStream_t st, const int32_t* page_table, int pt_stride, const int32_t* finished) {
@@ -653,6 +793,20 @@ void self_attention_decode(const T* q, int64_t q_stride, const T* kv, int64_t kv
     // early: old cache rows are fetched before the programmatic-dependency wait (only inside the decode step, where the row count
     // comes from the device-side position and rows below it are older than the previous kernel); TWB200_SA_EARLY=0 switches it off
     static const bool early_on = !(getenv("TWB200_SA_EARLY") && atoi(getenv("TWB200_SA_EARLY")) == 0);
+    // ring variant (cp.async into shared memory, 8 rows in flight per warp all the time): bf16 default; TWB200_SA_RING=0 / 1 forces
+    static const int ring_env = getenv("TWB200_SA_RING") ? atoi(getenv("TWB200_SA_RING")) : -1;
+    const bool ring = ring_env >= 0 ? ring_env != 0 : sizeof(T) == 2;
+    if (ring) {
+        constexpr int smem = SA_WARPS * SA_RING * 2 * 32 * 8 * (int)sizeof(T);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(self_attention_decode_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        launch_k(self_attention_decode_ring_kernel<T>, grid, dim3(SA_WARPS * 32), smem, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
+                 page_table, pt_stride, finished, (early_on && d_tk) ? 1 : 0);
+        return;
+    }
     launch_k(self_attention_decode_kernel<T, 4>, grid, dim3(SA_WARPS * 32), 0, st, q, q_stride, kv, kv_clip_stride, Tk, d_tk, H, out,
              page_table, pt_stride, finished, (early_on && d_tk) ? 1 : 0);
 }

@@ -1,12 +1,12 @@
 """In-graph cost of a decoder layer per token at large-v3 width, by row count: decode-only runs (CUDA graph + PDL) of a model
-with 1 encoder and N_DEC decoder layers, swept over row counts (ROWS=64,128) and TWB200_SKIP masks.
+with 1 encoder and N_DEC decoder layers, swept over row counts (ROWS=64,128) and TWB200_SKIP masks (MASKS=0,2 restricts them; TOKENS=252 for the bench's positions).
     python tools/decode_costs.py
 Leaving a kernel out gives its marginal cost inside the step (profiles/r02_decode_step_costs.md); results of masked runs are garbage."""
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_DEC, TOKENS = 8, 124
+N_DEC, TOKENS = 8, int(os.environ.get("TOKENS", "124"))
 
 import torch
 sys.path.insert(0, ROOT)
@@ -17,6 +17,8 @@ from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration  # noqa
 names = {0: "nothing", 1: "3 LayerNorms", 2: "self-attention", 4: "cross stream + combine", 8: "QKV", 16: "self out-proj", 32: "cross q",
          64: "cross out-proj", 128: "fc1", 256: "fc2", 504: "all six GEMMs"}
 rows_list = [int(x) for x in os.environ.get("ROWS", "64,128").split(",")]
+if os.environ.get("MASKS"):
+    names = {int(k): names.get(int(k), f"mask {k}") for k in os.environ["MASKS"].split(",")}
 sh = WhisperShape("lv3-8dec", 128, 1280, 5120, 20, 1, N_DEC, 51866)
 with torch.device("cuda"):
     hf = build_hf_model(sh, seed=1)
