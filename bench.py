@@ -616,9 +616,9 @@ def main():
             sms = None
             pipeline = {"unavailable": f"{type(ex).__name__}: {ex}"}
         if sms:
-            def timed_pipeline(batches_fn):
+            def timed_pipeline(batches_fn, auto_sms=False):
                 # a pipelined step = G batches of B clips: G stage-1 passes and ONE merged decode over G * B rows
-                gen = model.transcribe_batches((batches_fn(i) for i in range((W + K + 1) * G)), args.max_length, merge=G)
+                gen = model.transcribe_batches((batches_fn(i) for i in range((W + K + 1) * G)), args.max_length, merge=G, auto_sms=auto_sms)
                 for _ in range(W * G):
                     next(gen)
                 barrier()
@@ -662,9 +662,18 @@ def main():
                 bud = np.random.default_rng(0).integers(16, n_gen + 1, size=B * G)
                 model.set_row_budgets(bud.tolist())
                 r_ms, _, _ = timed_pipeline(lambda i: dev_batches[i % len(dev_batches)])
-                model.set_row_budgets(None)
                 ragged["pipelined"] = {"ms_per_step": r_ms / K, "clips_per_step": B * G, "value": K * B * G * CLIP_SECONDS / (r_ms / 1000.0),
-                                       "unit": "audio-s/s", "generated_tokens": int(bud.sum()), "full_budget_tokens": int(B * G * n_gen)}
+                                       "unit": "audio-s/s", "generated_tokens": int(bud.sum()), "full_budget_tokens": int(B * G * n_gen),
+                                       "encoder_sms": model.pipeline_sms[0]}
+                # rows that end early shift the balance towards stage 1: the same loop with the balance controller (auto_sms=True; it
+                # settles during the warm-up groups), then back to the headline's split
+                model.sms_history = []
+                ra_ms, _, _ = timed_pipeline(lambda i: dev_batches[i % len(dev_batches)], auto_sms=True)
+                ragged["pipelined_auto_sms"] = {"ms_per_step": ra_ms / K, "clips_per_step": B * G,
+                                                "value": K * B * G * CLIP_SECONDS / (ra_ms / 1000.0), "unit": "audio-s/s",
+                                                "encoder_sms": model.pipeline_sms[0], "resizes": [list(x) for x in model.sms_history]}
+                model.set_row_budgets(None)
+                model.enable_pipeline(sms[0])
             if not args.no_e2e:
                 pe_ms, _, _ = timed_pipeline(lambda i: host_batches[i % len(host_batches)])
                 e2e = {"value": world * K * B * G * CLIP_SECONDS / (pe_ms / 1000.0), "unit": "audio-s/s",

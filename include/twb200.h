@@ -158,6 +158,12 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
  * two CUDA green contexts (driver-level SM partitions); stage 1 runs in the small one, stage 2 in the rest.
  *   tw_pipeline_enable   n_enc_sms SMs (8 .. half the device; the driver rounds to its granularity) for stage 1; allocates the second
  *                        encoder-output / K|V-store pair.  TW_E_UNSUPPORTED when the driver has no green contexts.
+ *   tw_pipeline_resize   moves the boundary between the two partitions (both stages are drained first; batches already staged in a slot
+ *                        stay valid).  The balance depends on the workload: full-length rows (252 tokens) keep the decode partition busy
+ *                        ~7x longer than stage 1 needs the GPU, rows that end early (real audio) shift work towards stage 1.
+ *   tw_pipeline_stage_ms device time of the slot's last stage 1 (all parts of the group) and of its last decode, each measured inside its
+ *                        partition while the other stage runs; -1 for a stage that has not completed.  Never blocks: the input of a
+ *                        balance controller (host.py transcribe_batches(auto_sms=True)).
  *   tw_pipeline_encode   ASYNCHRONOUS stage 1 of a batch into slot 0 / 1: copy of int16 PCM [B, 480000] (host — it must stay valid until
  *                        the matching tw_pipeline_decode returns — or device), log-mel, encoder, cross-K/V.  Waits (on the device)
  *                        for the decode that last used the slot.
@@ -171,7 +177,9 @@ TW_API int tw_transcribe_host(tw_model* m, const int16_t* pcm_host, const int32_
  * Use: encode(b0, 0); for i: { encode(b[i+1], (i+1)&1); decode(i&1) -> ids of b[i] }.  Ids equal tw_transcribe_host's up to the
  * bf16 rounding of a different row split of the K|V stream. */
 TW_API int tw_pipeline_enable(tw_model* m, int n_enc_sms);
+TW_API int tw_pipeline_resize(tw_model* m, int n_enc_sms);
 TW_API int tw_pipeline_info(const tw_model* m, int* n_enc_sms, int* n_dec_sms);
+TW_API int tw_pipeline_stage_ms(tw_model* m, int slot, float* stage1_ms, float* decode_ms);
 TW_API int tw_pipeline_encode(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot);
 TW_API int tw_pipeline_encode_at(tw_model* m, const int16_t* pcm, const int32_t* n_valid_host, int B, int slot, int clip0);
 TW_API int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int P, const tw_rules* rules, int max_length,

@@ -159,6 +159,9 @@ struct tw_model {
         void* enc_out[2] = {nullptr, nullptr};
         void* xkv[2] = {nullptr, nullptr};
         cudaEvent_t enc_done[2] = {nullptr, nullptr}, dec_done[2] = {nullptr, nullptr};
+        // per-slot stage timing (tw_pipeline_stage_ms): stage 1 of the slot's group (first part's start .. last part's end), its decode
+        cudaEvent_t enc_t0[2] = {nullptr, nullptr}, enc_t1[2] = {nullptr, nullptr}, dec_t0[2] = {nullptr, nullptr}, dec_t1[2] = {nullptr, nullptr};
+        bool enc_timed[2] = {false, false}, dec_timed[2] = {false, false};
         bool dec_pending[2] = {false, false};
         bool in_decode = false;
     } pipe;
@@ -978,6 +981,8 @@ int tw_model_load(tw_ctx* ctx, const tw_model_desc* desc, const tw_weight* table
     return TW_OK;
 }
 
+namespace { void pipeline_drop_partitions(tw_model* m); }
+
 void tw_model_free(tw_model* m) {
     if (!m) return;
     for (void* p : m->allocs) cudaFree(p);
@@ -991,16 +996,10 @@ void tw_model_free(tw_model* m) {
         for (int i = 0; i < 2; ++i) {
             if (m->pipe.enc_done[i]) cudaEventDestroy(m->pipe.enc_done[i]);
             if (m->pipe.dec_done[i]) cudaEventDestroy(m->pipe.dec_done[i]);
+            for (cudaEvent_t e : {m->pipe.enc_t0[i], m->pipe.enc_t1[i], m->pipe.dec_t0[i], m->pipe.dec_t1[i]})
+                if (e) cudaEventDestroy(e);
         }
-        for (cudaStream_t s : {m->pipe.s_enc, m->pipe.s_dec, m->pipe.s_cap})
-            if (s) cudaStreamDestroy(s);
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && fn) {
-            auto destroy = reinterpret_cast<CUresult (*)(CUgreenCtx)>(fn);
-            if (m->pipe.g_enc) destroy(m->pipe.g_enc);
-            if (m->pipe.g_dec) destroy(m->pipe.g_dec);
-        }
+        pipeline_drop_partitions(m);
     }
     for (auto& ev : m->ev)
         if (ev) cudaEventDestroy(ev);
@@ -1200,10 +1199,10 @@ void set_active_sms(tw_model* m, int n) {
 }
 }  // namespace
 
-int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
-    if (!check_model(m, "tw_pipeline_enable")) return TW_E_INVALID;
+namespace {
+// SM partitions of the pipeline: two green contexts (n_enc_sms SMs / the rest) and their streams
+int pipeline_make_partitions(tw_model* m, int n_enc_sms) {
     tw_ctx* ctx = m->ctx;
-    if (m->pipe.on) return TW_OK;
     auto pGetRes = reinterpret_cast<PfnGetDevResource>(driver_entry("cuDeviceGetDevResource"));
     auto pSplit = reinterpret_cast<PfnSmSplit>(driver_entry("cuDevSmResourceSplitByCount"));
     auto pDesc = reinterpret_cast<PfnGenDesc>(driver_entry("cuDevResourceGenerateDesc"));
@@ -1229,8 +1228,6 @@ int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
     unsigned nb = 1;
     r = pSplit(&small, &nb, &all, &rest, 0, (unsigned)n_enc_sms);
     if (r != CUDA_SUCCESS || nb != 1) return fail("cuDevSmResourceSplitByCount", r);
-    P.n_enc = (int)small.sm.smCount;
-    P.n_dec = (int)rest.sm.smCount;
     CUdevResourceDesc d_small, d_rest;
     if ((r = pDesc(&d_small, &small, 1)) != CUDA_SUCCESS || (r = pDesc(&d_rest, &rest, 1)) != CUDA_SUCCESS) return fail("cuDevResourceGenerateDesc", r);
     if ((r = pCreate(&P.g_enc, d_small, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) return fail("cuGreenCtxCreate", r);
@@ -1239,9 +1236,33 @@ int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
     if ((r = pStream(&se, P.g_enc, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS || (r = pStream(&sd, P.g_dec, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS ||
         (r = pStream(&sc, P.g_dec, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS)
         return fail("cuGreenCtxStreamCreate", r);
+    P.n_enc = (int)small.sm.smCount;
+    P.n_dec = (int)rest.sm.smCount;
     P.s_enc = (cudaStream_t)se;
     P.s_dec = (cudaStream_t)sd;
     P.s_cap = (cudaStream_t)sc;
+    return TW_OK;
+}
+void pipeline_drop_partitions(tw_model* m) {
+    auto& P = m->pipe;
+    for (cudaStream_t* s : {&P.s_enc, &P.s_dec, &P.s_cap}) {
+        if (*s) cudaStreamDestroy(*s);
+        *s = nullptr;
+    }
+    if (auto destroy = reinterpret_cast<CUresult (*)(CUgreenCtx)>(driver_entry("cuGreenCtxDestroy"))) {
+        if (P.g_enc) destroy(P.g_enc);
+        if (P.g_dec) destroy(P.g_dec);
+    }
+    P.g_enc = P.g_dec = nullptr;
+}
+}  // namespace
+
+int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
+    if (!check_model(m, "tw_pipeline_enable")) return TW_E_INVALID;
+    tw_ctx* ctx = m->ctx;
+    if (m->pipe.on) return TW_OK;
+    auto& P = m->pipe;
+    TW_CHECK(pipeline_make_partitions(m, n_enc_sms));
     // second set of the buffers the two stages hand over: encoder output and cross-attention K|V store
     const tw_model_desc& D = m->desc;
     const size_t M = (size_t)D.max_batch * TW_N_CTX, d = D.d_model, e = m->esz;
@@ -1252,8 +1273,57 @@ int tw_pipeline_enable(tw_model* m, int n_enc_sms) {
     for (int i = 0; i < 2; ++i) {
         TW_CUDA_OK(ctx, cudaEventCreateWithFlags(&P.enc_done[i], cudaEventDisableTiming));
         TW_CUDA_OK(ctx, cudaEventCreateWithFlags(&P.dec_done[i], cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&P.enc_t0[i], &P.enc_t1[i], &P.dec_t0[i], &P.dec_t1[i]}) TW_CUDA_OK(ctx, cudaEventCreate(e));
     }
     P.on = true;
+    return TW_OK;
+}
+
+int tw_pipeline_resize(tw_model* m, int n_enc_sms) {
+    if (!check_model(m, "tw_pipeline_resize")) return TW_E_INVALID;
+    tw_ctx* ctx = m->ctx;
+    auto& P = m->pipe;
+    if (!P.on) {
+        ctx->set_error(TW_E_INVALID, "tw_pipeline_resize: pipeline not enabled");
+        return TW_E_INVALID;
+    }
+    // both stages drained (a batch staged in a slot stays valid: the buffers do not move), the decode graphs captured in the
+    // old decode partition dropped (a graph's kernel nodes run in the context of its capture stream)
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(P.s_enc));
+    TW_CUDA_OK(ctx, cudaStreamSynchronize(P.s_dec));
+    for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second.exec);
+    m->graphs.clear();
+    const int old_enc = P.n_enc;
+    pipeline_drop_partitions(m);
+    int r = pipeline_make_partitions(m, n_enc_sms);
+    if (r != TW_OK) {
+        // keep the pipeline usable: back to the previous split
+        const std::string msg = ctx->err;
+        pipeline_drop_partitions(m);
+        if (pipeline_make_partitions(m, old_enc) != TW_OK) P.on = false;
+        ctx->set_error(r, msg);
+        return r;
+    }
+    return TW_OK;
+}
+
+int tw_pipeline_stage_ms(tw_model* m, int slot, float* stage1_ms, float* decode_ms) {
+    if (!check_model(m, "tw_pipeline_stage_ms")) return TW_E_INVALID;
+    auto& P = m->pipe;
+    if (!P.on || slot < 0 || slot > 1) {
+        m->ctx->set_error(TW_E_INVALID, "tw_pipeline_stage_ms: pipeline not enabled or bad slot");
+        return TW_E_INVALID;
+    }
+    // never blocks: a stage that has not completed (or was never run) reads as -1
+    if (stage1_ms) {
+        *stage1_ms = -1.0f;
+        if (P.enc_timed[slot] && cudaEventQuery(P.enc_t1[slot]) == cudaSuccess) cudaEventElapsedTime(stage1_ms, P.enc_t0[slot], P.enc_t1[slot]);
+    }
+    if (decode_ms) {
+        *decode_ms = -1.0f;
+        if (P.dec_timed[slot] && cudaEventQuery(P.dec_t1[slot]) == cudaSuccess) cudaEventElapsedTime(decode_ms, P.dec_t0[slot], P.dec_t1[slot]);
+    }
+    cudaGetLastError();      // cudaErrorNotReady of a query is not an error of the library
     return TW_OK;
 }
 
@@ -1291,6 +1361,7 @@ int tw_pipeline_encode_at(tw_model* m, const int16_t* pcm, const int32_t* n_vali
     int r = TW_OK;
     do {
         cudaEventRecord(m->ev[6], st);
+        if (clip0 == 0) { cudaEventRecord(P.enc_t0[slot], st); P.enc_timed[slot] = false; }
         if (cudaMemcpyAsync(m->ws_pcm, pcm, (size_t)B * TW_N_SAMPLES * sizeof(int16_t), cudaMemcpyDefault, st) != cudaSuccess) { r = TW_E_CUDA; break; }
         const int32_t* nv = nullptr;
         if (n_valid_host) {
@@ -1311,6 +1382,8 @@ int tw_pipeline_encode_at(tw_model* m, const int16_t* pcm, const int32_t* n_vali
         if (r != TW_OK) break;
         cudaEventRecord(m->ev[3], st);
         if (cudaEventRecord(P.enc_done[slot], st) != cudaSuccess) { r = TW_E_CUDA; break; }
+        cudaEventRecord(P.enc_t1[slot], st);
+        P.enc_timed[slot] = true;
     } while (0);
     m->xkv = xkv_before;
     set_active_sms(m, sms_before);
@@ -1342,6 +1415,8 @@ int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int 
     m->absorb_now = use_absorb(m, B);
     P.in_decode = true;
     cudaEventRecord(m->ev[7], st);
+    cudaEventRecord(P.dec_t0[slot], st);
+    P.dec_timed[slot] = false;
     int r = D.dtype == TW_BF16
                 ? decode_impl<__nv_bfloat16>(m, B, prompt, P_len, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st)
                 : decode_impl<float>(m, B, prompt, P_len, R, max_length, m->d_out_tok, m->d_out_len, nullptr, nullptr, 0, st);
@@ -1352,6 +1427,8 @@ int tw_pipeline_decode(tw_model* m, int slot, int B, const int32_t* prompt, int 
     TW_CUDA_OK(ctx, cudaMemcpyAsync(out_tokens_host, m->d_out_tok, (size_t)B * n_gen * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     TW_CUDA_OK(ctx, cudaMemcpyAsync(out_lengths_host, m->d_out_len, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     cudaEventRecord(m->ev[4], st);
+    cudaEventRecord(P.dec_t1[slot], st);
+    P.dec_timed[slot] = true;
     TW_CUDA_OK(ctx, cudaEventRecord(P.dec_done[slot], st));
     P.dec_pending[slot] = true;
     TW_CUDA_OK(ctx, cudaStreamSynchronize(st));

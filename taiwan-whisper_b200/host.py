@@ -613,16 +613,40 @@ class B200WhisperForConditionalGeneration:
     def enable_pipeline(self, n_enc_sms: int = 24):
         """Splits the GPU into two SM partitions (CUDA green contexts): `n_enc_sms` SMs for the front end + encoder + cross-K/V
         of the NEXT batch, the rest for the greedy decode of the current one (`transcribe_batches`).  Returns (encoder SMs,
-        decode SMs) as the driver granted them.  Raises NotImplementedError when the driver has no green contexts."""
+        decode SMs) as the driver granted them (multiples of 8).  Calling it again moves the boundary (tw_pipeline_resize).
+        Raises NotImplementedError when the driver has no green contexts."""
         with torch.cuda.device(self.device):
-            self.ctx.check(self.ctx.lib.tw_pipeline_enable(C.c_void_p(self.handle), int(n_enc_sms)))
+            if getattr(self, "pipeline_sms", None):
+                self.ctx.check(self.ctx.lib.tw_pipeline_resize(C.c_void_p(self.handle), int(n_enc_sms)))
+            else:
+                self.ctx.check(self.ctx.lib.tw_pipeline_enable(C.c_void_p(self.handle), int(n_enc_sms)))
         a, b = C.c_int(0), C.c_int(0)
         self.ctx.check(self.ctx.lib.tw_pipeline_info(C.c_void_p(self.handle), C.byref(a), C.byref(b)))
         self.pipeline_sms = (a.value, b.value)
         return self.pipeline_sms
 
+    def pipeline_stage_ms(self, slot: int):
+        """(stage-1 ms, decode ms) of the slot's last group, each measured in its partition while the other stage runs; -1 for a
+        stage that has not completed.  Never blocks."""
+        a, b = C.c_float(-1), C.c_float(-1)
+        self.ctx.check(self.ctx.lib.tw_pipeline_stage_ms(C.c_void_p(self.handle), int(slot), C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    @staticmethod
+    def _balanced_sms(n_enc: int, n_dev: int, t_enc: float, t_dec: float) -> int:
+        """Encoder-partition size for the next groups from the measured stage times of the last one.  Stage 1 scales ~1 / SMs;
+        the decode is HBM-bound and loses little from a smaller partition, so the rule only asks that stage 1 finishes a little
+        before the decode does (target 0.92 of its time) and leaves a wide dead band (0.75 .. 1.02) against oscillation."""
+        if t_enc <= 0 or t_dec <= 0:
+            return n_enc
+        ratio = t_enc / t_dec
+        want = n_enc
+        if ratio > 1.02 or ratio < 0.75:
+            want = int(-(-n_enc * ratio / 0.92 // 8) * 8)          # rounded up to the partition granularity
+        return max(16, min(want, (n_dev // 2) // 8 * 8))
+
     def transcribe_batches(self, batches, max_length: int, return_timestamps: bool = False, language="zh", task="transcribe",
-                           merge: int = 1):
+                           merge: int = 1, auto_sms: bool = False):
         """The reference's batch loop (ref training/run_pseudo_labelling.py:915-918) as a generator: yields (tokens, lengths) — pinned
         host int32 tensors [B, max_length - P] / [B] — for every int16 PCM batch [B, 480000] of `batches` (pinned host or device
         tensors), in order.  While batch i decodes, batch i+1 is already in its log-mel / encoder / cross-K/V stage on the other SM
@@ -633,7 +657,12 @@ class B200WhisperForConditionalGeneration:
         over all rows.  A decode step streams the decoder weights and runs its chain of small dependent kernels once whatever
         the row count, so merged batches pay them once; per row nothing changes (same kernels, same arithmetic per row: ids equal
         the unmerged loop's up to the bf16 rounding of a different K|V row split).  The model needs max_batch >= the merged rows;
-        results are still yielded per input batch."""
+        results are still yielded per input batch.
+
+        `auto_sms=True` re-balances the two partitions while the loop runs: after every group the stage times of the last one
+        (tw_pipeline_stage_ms) are compared and the encoder partition is resized when stage 1 has become the bottleneck or idles
+        more than a quarter of the time (`_balanced_sms`).  Full-length rows keep the decode busy ~7x longer than stage 1 needs the
+        GPU; rows that end early (real audio) shift the balance towards stage 1 — the right split depends on the data."""
         if not getattr(self, "pipeline_sms", None):
             raise RuntimeError("transcribe_batches needs enable_pipeline() first")
         if merge < 1:
@@ -680,6 +709,19 @@ class B200WhisperForConditionalGeneration:
                 out_lengths = torch.empty((B,), dtype=torch.int32).pin_memory()
                 self.ctx.check(lib.tw_pipeline_decode(h, i & 1, B, p, len(prompt), C.byref(rules), max_length, out_tokens.data_ptr(),
                                                       out_lengths.data_ptr()))
+                if auto_sms and nxt is not None and sum(nxt[0]) == B:
+                    # stage 1 of the NEXT group ran beside this decode: both times are of the same concurrent interval
+                    t_enc, _ = self.pipeline_stage_ms((i + 1) & 1)
+                    _, t_dec = self.pipeline_stage_ms(i & 1)
+                    if t_enc > 0 and t_dec > 0:          # (stage 1 still running: it is the bottleneck by at least this much)
+                        want = self._balanced_sms(self.pipeline_sms[0], sum(self.pipeline_sms), t_enc, t_dec)
+                    elif t_dec > 0:
+                        want = self._balanced_sms(self.pipeline_sms[0], sum(self.pipeline_sms), 1.25 * t_dec, t_dec)
+                    else:
+                        want = self.pipeline_sms[0]
+                    if want != self.pipeline_sms[0]:
+                        self.enable_pipeline(want)
+                        self.sms_history = getattr(self, "sms_history", []) + [self.pipeline_sms]
                 b0 = 0
                 for n in cur[0]:
                     yield out_tokens[b0:b0 + n], out_lengths[b0:b0 + n]

@@ -19,7 +19,7 @@ EXPORTS = [
     "tw_model_load", "tw_model_free", "tw_model_bytes", "tw_model_get_desc", "tw_workspace_bytes", "tw_encode", "tw_decode_greedy", "tw_transcribe_host",
     "tw_last_stage_ms", "tw_debug_gemm", "tw_profile", "tw_debug_set_pdl", "tw_debug_set_row_budgets", "tw_decoder_logits", "tw_debug_attention", "tw_debug_self_attention_paged",
     "tw_debug_decode_attention", "tw_debug_encoder_attention", "tw_debug_self_attention", "tw_debug_gemm_grouped",
-    "tw_debug_absorbed_attention", "tw_pipeline_enable", "tw_pipeline_info", "tw_pipeline_encode", "tw_pipeline_encode_at", "tw_pipeline_decode",
+    "tw_debug_absorbed_attention", "tw_pipeline_enable", "tw_pipeline_resize", "tw_pipeline_info", "tw_pipeline_stage_ms", "tw_pipeline_encode", "tw_pipeline_encode_at", "tw_pipeline_decode",
 ]
 
 
@@ -93,6 +93,8 @@ def load_library() -> C.CDLL:
     lib.tw_debug_gemm_grouped.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     lib.tw_debug_absorbed_attention.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     lib.tw_pipeline_enable.argtypes = [vp, C.c_int]
+    lib.tw_pipeline_resize.argtypes = [vp, C.c_int]
+    lib.tw_pipeline_stage_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.tw_pipeline_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.tw_pipeline_encode.argtypes = [vp, vp, vp, C.c_int, C.c_int]
     lib.tw_pipeline_encode_at.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]

@@ -695,6 +695,21 @@ def test_pipelined_batch_loop_matches_sequential(dtype_name):
                 else:
                     agree = (toks[j] == st[j]).float().mean().item()
                     assert toks[j, :4].tolist() == st[j, :4].tolist() and agree >= 0.5, (merge, o, j, agree)
+    # moving the partition boundary (tw_pipeline_resize) and the balance controller: same ids whatever the split
+    sms2 = m.enable_pipeline(32)
+    assert sms2[0] == 32 and sms2[0] + sms2[1] == sms[0] + sms[1]
+    assert m.pipeline_stage_ms(0)[0] != 0.0
+    for auto in (False, True):
+        got = list(m.transcribe_batches(sb, max_length, merge=2, auto_sms=auto))
+        for o, (toks, lens), (st, sl) in zip(small, got, sseq):
+            assert lens.tolist() == sl.tolist()
+            for j, b in enumerate(o):
+                if dtype_name == "f32":
+                    assert toks[j].tolist() == ora[b]["tokens"][:n], (auto, o, j)
+                else:
+                    assert toks[j, :4].tolist() == st[j, :4].tolist(), (auto, o, j)
+    t_enc, t_dec = m.pipeline_stage_ms(0)
+    assert t_enc > 0 and t_dec > 0
     # the one-call path still works on the whole GPU afterwards
     t2, _ = m.transcribe_pcm(host[orders[0]].pin_memory(), max_length)
     assert t2.tolist() == seq[0][0].tolist()
