@@ -453,6 +453,9 @@ def run_longform(args, rank, world, local_rank):
 
 
 def main():
+    import faulthandler
+    import signal
+    faulthandler.register(signal.SIGUSR1, all_threads=True)      # `kill -USR1` prints where a stuck run is (Python frames) and carries on
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

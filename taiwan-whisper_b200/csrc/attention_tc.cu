@@ -77,24 +77,6 @@ __device__ __forceinline__ float fa_ex2(float x) {           // single MUFU.EX2 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^x on the FMA / ALU pipes (FlashAttention-4's split of the exponentials): round-to-nearest split x = n + f, |f| <= 0.5, a cubic for
-// 2^f (max relative error 7.5e-5, a twentieth of bf16's rounding step — P is rounded to bf16 right after), n added to the
-// exponent field.  x <= 8 by the lazy reference max; very negative x is clamped (the result is then ~1e-38: zero in bf16).
-// Nine FP32 / integer instructions against one MUFU.EX2 — but the MUFU pipe issues 16 per clock per SM and is what paces the
-// softmax warps at head_dim 64, so every POLY-th score goes this way.
-__device__ __forceinline__ float fa_ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;                  // 1.5 * 2^23: n = round(x) sits in the low mantissa bits
-    const float f = x - (t - 12582912.0f);
-    float p = fmaf(0.0551716648042202f, f, 0.2426111251115799f);
-    p = fmaf(p, f, 0.6932609677314758f);
-    p = fmaf(p, f, 0.9999280571937561f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-template <int POLY> __device__ __forceinline__ float fa_exp_sel(float x, int i) {
-    if (POLY > 0 && (i % POLY) == POLY - 1) return fa_ex2_poly(x);
-    return fa_ex2(x);
-}
 // one elected lane of a converged warp (see tc_ptx.cuh: the single-thread roles run warp-uniform and issue under this predicate)
 __device__ __forceinline__ uint32_t fa_elect() {
     uint32_t pred = 0;
@@ -180,14 +162,14 @@ __device__ __forceinline__ float fa_max3(float a, float b, float c) {
 //   MMA issue order:  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...     (P(j) overwrites the first 32 columns of S(j&1); QK(j+2)
 //   is issued after PV(j), and the tensor pipe executes in order).  O / L are rescaled (rarely) only after pv_done(j-1).
 // Measured (B200, 20 heads x 1500 keys, batch 8): 591 TFLOP/s; also tried and dropped: 128-key tiles without the double
-// buffer (518), eight softmax warps per CTA sharing rows through shared memory (555).
-constexpr int FA_POLY_DEFAULT = 4;       // measured: 584 (0) / 631 (4) / 628 (3) / 588 (2) TFLOP/s at 20 heads x 1500 keys
+// buffer (518), eight softmax warps per CTA sharing rows through shared memory (555), every 4th exponential as an FMA-pipe
+// cubic instead of MUFU.EX2 (631 alone and test-green, but the pipelined batch loop hung with it on the 24-SM partition:
+// profiles/r02_encoder_attention_ncu.md, addendum 2).
 constexpr int FA3_BK = 64;
 constexpr int FA3_KV_BYTES = FA3_BK * FA_D * 2;       // 8 KB
 constexpr int FA3_STAGES = 4;
 constexpr int FA3_SMEM = 1024 + FA_TILE_BYTES + FA3_KV_BYTES * (2 * FA3_STAGES + 1) + 512;    // Q, K x4, V x4, ones
 
-template <int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                              __nv_bfloat16* __restrict__ out, int S, int Sk, int H, int q_col0, int k_col0, int v_col0, int causal) {
@@ -402,14 +384,14 @@ encoder_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __g
             if (full_tile) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_exp_sel<POLY>(fmaf(__uint_as_float(va[i]), LOG2E, mneg), i),
-                                                              fa_exp_sel<POLY>(fmaf(__uint_as_float(va[i + 1]), LOG2E, mneg), i + 1));
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_ex2(fmaf(__uint_as_float(va[i]), LOG2E, mneg)),
+                                                              fa_ex2(fmaf(__uint_as_float(va[i + 1]), LOG2E, mneg)));
                     pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hb);
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_exp_sel<POLY>(fmaf(__uint_as_float(vb[i]), LOG2E, mneg), i),
-                                                              fa_exp_sel<POLY>(fmaf(__uint_as_float(vb[i + 1]), LOG2E, mneg), i + 1));
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(fa_ex2(fmaf(__uint_as_float(vb[i]), LOG2E, mneg)),
+                                                              fa_ex2(fmaf(__uint_as_float(vb[i + 1]), LOG2E, mneg)));
                     pk[16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&hb);
                 }
             } else {
@@ -522,10 +504,7 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
             return TW_E_CUDA;
         }
         g_fa_encode = reinterpret_cast<FaEncodeTiledFn>(fn);
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        TW_CUDA_OK(ctx, cudaFuncSetAttribute(encoder_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
     }
     if (causal && Sq != Sk) {
         ctx->set_error(TW_E_INVALID, "attention_tc: the causal mask needs as many queries as keys");
@@ -535,11 +514,8 @@ int attention_tc(tw_ctx* ctx, const __nv_bfloat16* q, int64_t q_ld, int q_col0, 
     TW_CHECK(fa_map(ctx, q, B * Sq, q_ld, &mq));
     TW_CHECK(fa_map(ctx, kv, B * Sk, kv_ld, &mkv, FA3_BK));
     dim3 grid(ceil_div(Sq, FA_BQ), H, B);
-    // every POLY-th exponential on the FMA pipes (0 = all on MUFU); TWB200_FA_POLY = 0 / 2 / 3 / 4
-    static const int poly = getenv("TWB200_FA_POLY") ? atoi(getenv("TWB200_FA_POLY")) : FA_POLY_DEFAULT;
-    auto kern = poly == 2 ? encoder_attention_tc_kernel<2> : poly == 3 ? encoder_attention_tc_kernel<3>
-              : poly == 4 ? encoder_attention_tc_kernel<4> : encoder_attention_tc_kernel<0>;
-    TW_CUDA_OK(ctx, launch_k(kern, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0, causal ? 1 : 0));
+    TW_CUDA_OK(ctx, launch_k(encoder_attention_tc_kernel, grid, dim3(FA_THREADS), FA3_SMEM, st, mq, mkv, out, Sq, Sk, H, q_col0, k_col0, v_col0,
+                             causal ? 1 : 0));
     TW_CUDA_OK(ctx, cudaGetLastError());
     return TW_OK;
 }
