@@ -360,7 +360,8 @@ int gemm_tc_skinny(tw_ctx* ctx, const __nv_bfloat16* A, int64_t lda, const __nv_
     // (vocabulary head) take 128-wide tiles.  The residual epilogue splits K (fp32 atomics) only as far as idle SMs remain: a
     // cost model that traded wider tiles for deeper splits (more CTAs, shorter K loops) measured 3-5 % SLOWER per decoder layer
     // at 64 and 128 rows — the extra atomic traffic on the residual stream costs more than the shorter loops save
-    // (profiles/r02_merged_decode.md).  TWB200_SK_BN forces a width.
+    // (profiles/r02_merged_decode.md); so did 64-wide tiles with a two-way split for the unsplit residual GEMMs of merged batches
+    // (fc2 alone 10.5 -> 7.2 us at 192 rows, the whole layer 308 -> 310 us).  TWB200_SK_BN forces a width.
     static const int force_bn = getenv("TWB200_SK_BN") ? atoi(getenv("TWB200_SK_BN")) : 0;
     const int mblocks = ceil_div(M, 64);
     const int kstages = ceil_div(K / 64, SK2_KSUB);

@@ -209,3 +209,25 @@ def test_workspace_bytes_is_host_arithmetic():
     assert nbytes(128, twlib.TW_BF16) > b64 > nbytes(32, twlib.TW_BF16)
     assert nbytes(64, twlib.TW_F32) > 1.9 * b64 - 1e9
     assert lib.tw_workspace_bytes(None) == 0
+
+
+def test_pipeline_balance_rule():
+    """transcribe_batches(auto_sms=True): encoder-partition size from the stage times of the last group (host.py _balanced_sms)."""
+    from taiwan_whisper_b200.host import B200WhisperForConditionalGeneration as M
+    # inside the dead band (stage 1 between 0.75 and 1.02 of the decode): no change
+    assert M._balanced_sms(24, 148, 2710.0, 3100.0) == 24
+    assert M._balanced_sms(40, 148, 1600.0, 1700.0) == 40
+    # stage 1 is the bottleneck: grow, in multiples of 8, never beyond half of the device
+    assert M._balanced_sms(24, 148, 2700.0, 1500.0) == 48
+    assert M._balanced_sms(24, 148, 9000.0, 1000.0) == 72
+    # stage 1 idles: shrink, never below 16
+    assert M._balanced_sms(48, 148, 800.0, 2500.0) == 24
+    assert M._balanced_sms(24, 148, 1000.0, 3100.0) == 16
+    assert M._balanced_sms(16, 148, 100.0, 3100.0) == 16
+    # a stage that was not measured leaves the split alone
+    assert M._balanced_sms(24, 148, -1.0, 3100.0) == 24
+    # the rule converges: applying it to times that scale ~1 / SMs settles in one or two moves
+    n, work, t_dec = 24, 24 * 2700.0, 1500.0
+    for _ in range(4):
+        n = M._balanced_sms(n, 148, work / n, t_dec)
+    assert n == M._balanced_sms(n, 148, work / n, t_dec) and 0.75 <= (work / n) / t_dec <= 1.02
