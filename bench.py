@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--workload", default="clips", choices=["clips", "longform"],
                     help="clips: BASELINE configs[1] (default); longform: configs[4] — long recordings cut into 30 s windows "
                          "(hop 20 s, stride 5 s each side), timestamp mode, windows batched, timestamp-aware stitching")
+    ap.add_argument("--longform-merge", type=int, default=5,
+                    help="--workload longform: encoder batches of `batch` windows decoded together (one greedy decode over batch x merge rows)")
     ap.add_argument("--recordings", type=int, default=10)
     ap.add_argument("--recording-seconds", type=int, default=600)
     ap.add_argument("--ref-clips", type=int, default=0, help="--impl reference: clips per step (0 = sized from K + W)")
@@ -328,7 +330,8 @@ def run_longform(args, rank, world, local_rank):
     K, W = args.steps, args.warmup
     with torch.device(dev):
         hf = build_hf_model(sh, seed=1234)
-    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B, device=str(dev), output_layout="5.x")
+    G = max(1, args.longform_merge)          # encoder batches per decode (merged decode, as transcribe_batches(merge=) does for clips)
+    model = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.bfloat16, max_batch=B * G, device=str(dev), output_layout="5.x")
     del hf
     torch.cuda.empty_cache()
     n_rec, rec_s = args.recordings, args.recording_seconds
@@ -352,9 +355,13 @@ def run_longform(args, rank, world, local_rank):
         return torch.cat(feats), strides
 
     def decode_all(feats):
+        # windows go through the encoder `B` at a time (the reference pipeline's batch); G encoder batches are decoded together: a
+        # decode step streams the decoder weights and runs its chain of small kernels once whatever the row count
         toks, lens = [], []
-        for b0 in range(0, feats.shape[0], B):
-            enc = model.encode(feats[b0:b0 + B])
+        for g0 in range(0, feats.shape[0], B * G):
+            encs = [model.encode(feats[b0:b0 + B]) for b0 in range(g0, min(g0 + B * G, feats.shape[0]), B)]
+            enc = encs[0] if len(encs) == 1 else torch.cat(encs)
+            del encs
             t, l = model.decode(enc, prompt, max_length, True)
             toks.append(t)
             lens.append(l)
@@ -395,11 +402,12 @@ def run_longform(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     launches = model.ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    prof_ms, prof_n = 0.0, 0
+    prof_ms, prof_n, prof_rows = 0.0, 0, 0
     if rank == 0:
         model.profile(True)
-        f, st = windows(recs_dev[:1])
-        decode_all(f[:B])
+        f, st = windows(recs_dev[:max(1, -(-B * G // clips_per_rec))])
+        prof_rows = min(B * G, f.shape[0])          # one merged decode at the row count of the timed loop
+        decode_all(f[:prof_rows])
         torch.cuda.synchronize()
         prof_ms, prof_n = model.profile(False)
     t = torch.tensor([ms], device=dev)
@@ -424,7 +432,7 @@ def run_longform(args, rank, world, local_rank):
     if rank == 0:
         hbm, tf, which = peaks()
         n_gen = max_length - len(prompt)
-        bytes_per_launch = min(B, n_windows) * 1500 * 2 * sh.d_model * 2
+        bytes_per_launch = prof_rows * 1500 * 2 * sh.d_model * 2
         roof = None
         if prof_n > 0:
             ach = bytes_per_launch / (prof_ms / prof_n / 1000.0) / 1e9
@@ -436,9 +444,10 @@ def run_longform(args, rank, world, local_rank):
             "ms_per_step": float(ms) / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"whisper-{model_name} validator inference on long-form audio: {n_rec} x {rec_s} s recordings per GPU per "
-                                   f"step, 30 s windows hop 20 s (stride 5 s each side) = {n_windows} windows, batch {B}, timestamps on, "
+                                   f"step, 30 s windows hop 20 s (stride 5 s each side) = {n_windows} windows, encoder batches of {B}, "
+                                   f"{G} of them ({B * G} rows) per greedy decode, timestamps on, "
                                    f"max_length {max_length} ({n_gen} generated tokens/window), timestamp-aware stitching",
-                       "batch_per_gpu": B, "max_length": max_length, "weights": "random-init (HF init, seed 1234)",
+                       "batch_per_gpu": B, "decode_rows": B * G, "max_length": max_length, "weights": "random-init (HF init, seed 1234)",
                        "parallelism": f"recordings sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs larger than L2: every decode step streams > 4 GB of K/V and weights"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,

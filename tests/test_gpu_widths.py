@@ -441,6 +441,14 @@ def test_longform_config5_end_to_end():
         chunks = transcribe_longform(m, torch.from_numpy(rec).cuda(), max_length=max_length, special_ids=tok.all_special_ids)
     finally:
         m.close()
+    # encoder batches of 2 windows, both decoded together (merged decode): the same chunks
+    m = B200WhisperForConditionalGeneration.from_hf(hf, dtype=torch.float32, max_batch=4, output_layout="5.x")
+    try:
+        merged = transcribe_longform(m, torch.from_numpy(rec).cuda(), max_length=max_length, special_ids=tok.all_special_ids,
+                                     batch_size=2, merge=2)
+    finally:
+        m.close()
+    assert [(c["timestamp"], c["tokens"]) for c in merged] == [(c["timestamp"], c["tokens"]) for c in chunks]
     starts, strides = chunk_plan(len(rec))
     assert len(starts) == 4 and strides[0][1] == 0 and strides[-1][2] == 0
     P, rules = prompt_ids(sh.vocab, True), default_rules(sh.vocab, True)
