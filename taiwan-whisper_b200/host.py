@@ -677,20 +677,20 @@ class B200WhisperForConditionalGeneration:
         p = (C.c_int32 * len(prompt))(*prompt)
         lib, h = self.ctx.lib, C.c_void_p(self.handle)
         it = iter(batches)
+        pending = []                 # a batch that did not fit the current group
 
         def encode_group(slot):
             """Stage 1 of the next `merge` batches (fewer at the end of the loop, or when the next batch would not fit max_batch)
             into `slot`; returns the row count of each and keeps the PCM tensors alive until their decode has returned."""
             sizes, alive = [], []
             while len(sizes) < merge:
-                pcm = self._pending if self._pending is not None else next(it, None)
-                self._pending = None
+                pcm = pending.pop() if pending else next(it, None)
                 if pcm is None:
                     break
                 if pcm.dtype != torch.int16 or pcm.dim() != 2 or pcm.shape[1] != N_SAMPLES or pcm.shape[0] > self.max_batch or pcm.shape[0] == 0:
                     raise ValueError("transcribe_batches expects int16 tensors [1 <= B <= max_batch, 480000]")
                 if sum(sizes) + pcm.shape[0] > self.max_batch:
-                    self._pending = pcm                # opens the next group
+                    pending.append(pcm)                # opens the next group
                     break
                 pcm = pcm.contiguous()
                 self.ctx.check(lib.tw_pipeline_encode_at(h, pcm.data_ptr(), None, pcm.shape[0], slot, sum(sizes)))
@@ -698,7 +698,6 @@ class B200WhisperForConditionalGeneration:
                 alive.append(pcm)
             return (sizes, alive) if sizes else None
 
-        self._pending = None
         with torch.cuda.device(self.device):
             cur = encode_group(0)
             i = 0
