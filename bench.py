@@ -628,7 +628,7 @@ def main():
             sms = None
             pipeline = {"unavailable": f"{type(ex).__name__}: {ex}"}
         if sms:
-            def timed_pipeline(batches_fn, auto_sms=False):
+            def timed_pipeline(batches_fn, auto_sms=False, G=G):
                 # a pipelined step = G batches of B clips: G stage-1 passes and ONE merged decode over G * B rows
                 gen = model.transcribe_batches((batches_fn(i) for i in range((W + K + 1) * G)), args.max_length, merge=G, auto_sms=auto_sms)
                 for _ in range(W * G):
@@ -669,6 +669,13 @@ def main():
                                    f"whatever the row count), so a pipelined step = {B * G} clips; `sequential` is the strict one-batch-per-call loop"
                                    if G > 1 else ""),
                         "stage_ms_in_partition": model.last_stage_ms()}
+            if G > 1 and rank == 0 and world == 1:
+                # the same loop with ONE batch per decode (merge = 1) on its own best split (16 encoder SMs): what merging buys
+                model.enable_pipeline(16)
+                u_ms, _, _ = timed_pipeline(lambda i: dev_batches[i % len(dev_batches)], G=1)
+                pipeline["unmerged"] = {"merge": 1, "encoder_sms": model.pipeline_sms[0], "clips_per_step": B, "ms_per_step": u_ms / K,
+                                        "value": K * B * CLIP_SECONDS / (u_ms / 1000.0), "unit": "audio-s/s"}
+                model.enable_pipeline(sms[0])
             if ragged is not None:
                 # the ragged variant through the same pipelined / merged loop: budgets drawn per row of the merged batch
                 bud = np.random.default_rng(0).integers(16, n_gen + 1, size=B * G)
