@@ -136,6 +136,12 @@ NCU_TRAFFIC_CSV = {64: "r02_decode_attention_stream_raw.csv", 128: "r02_decode_a
                    192: "r02_decode_attention_stream_b192_raw.csv"}
 
 
+def workload_text(model, B, max_length, n_gen):
+    """The workload both arms name (BASELINE.json configs[1] at the defaults); each arm appends what one of ITS steps covers."""
+    return (f"whisper-{model} pseudo-labelling: batches of {B} x 30 s 16 kHz clips per GPU, log-mel + encoder + cross-K/V + greedy "
+            f"decode, zh/transcribe, max_length {max_length} ({n_gen} generated tokens/clip)")
+
+
 def ncu_traffic_bytes(rows=64):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same shape
     (profiles/r02_decode_attention_stream[_b128]_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum)."""
@@ -203,8 +209,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "rtfx_audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"whisper-{args.model} pseudo-labelling, {args.batch} x 30 s clips per GPU, greedy zh/transcribe, "
-                               f"max_length {args.max_length}", "sample": sample,
+        "config": {"workload": workload_text(args.model, args.batch, args.max_length, args.max_length - 4)
+                               + f"; a step = a bounded sample of {clips_per_step} clips (one HF batch on the host CPU)",
+                   "batch_per_gpu": args.batch, "clips_per_step": clips_per_step, "max_length": args.max_length,
+                   "weights": "random-init (HF init, seed 1234)", "sample": sample,
                    "reference": "transformers WhisperFeatureExtractor + WhisperForConditionalGeneration.generate on host CPU"},
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -760,9 +768,7 @@ def main():
             "metric": "rtfx_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"whisper-{args.model} pseudo-labelling: batches of {B} x 30 s 16 kHz clips per GPU, log-mel + "
-                                   f"encoder + cross-K/V + greedy decode, zh/transcribe, max_length {args.max_length} "
-                                   f"({n_gen} generated tokens/clip); a step = {G} batch(es) = {B * G} clips"
+            "config": {"workload": workload_text(args.model, B, args.max_length, n_gen) + f"; a step = {G} batch(es) = {B * G} clips"
                                    + (f" (pipelined loop, {G} batches decoded together)" if G > 1 else ""),
                        "batch_per_gpu": B, "clips_per_step": B * G, "max_length": args.max_length, "weights": "random-init (HF init, seed 1234)",
                        "parallelism": f"manifest sharded over {world} GPU(s), no data-path collective",
